@@ -1,0 +1,120 @@
+/* wise_b200.h - C-ABI of libwiseb200.so, the B200 (sm_100a) search-index backend for WISE.
+ *
+ * The reference (ox-vgg/wise) has no FFI: its hot path is the Python object protocol of the
+ * faiss CPU classes held in FeatureSearchIndex.index.  Every entry point below names the
+ * reference call it replaces (paths under /root/reference).  A maintainer binds these with
+ * ctypes; wise_b200/faiss_compat.py is that binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; wb_last_error() gives the
+ *     message of the last error on the calling thread.  Nothing throws across the boundary.
+ *   - the caller owns every buffer; "host" pointers are ordinary (pageable or pinned) host
+ *     memory, "_dev" variants take device pointers on the index's GPU and a cudaStream_t
+ *     (passed as void*) and do not synchronise.
+ *   - one index lives on one GPU (one process per GPU; rows are sharded across processes by
+ *     the host layer, wise_b200/sharded.py, which merges the per-GPU top-k with
+ *     wb_merge_topk_dev after an NCCL all-gather).
+ *   - results: D float32[nq*k] sorted by score descending, ties broken by lowest insertion
+ *     position; I int64[nq*k]; unfilled slots are (-FLT_MAX, -1) exactly like faiss.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef WISE_B200_H
+#define WISE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wb_index wb_index;
+
+#define WB_MAX_K 2048 /* top-k / nprobe limit of the fused selection (faiss-gpu has the same cap) */
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* wb_last_error(void);
+const char* wb_version(void);
+int wb_device_count(int* count);
+
+/* ---- construction ----------------------------------------------------------------------- */
+/* faiss.IndexFlatIP(d) [+ faiss.IndexIDMap(index)]   src/index/feature_search_index.py:47-52.
+ * One object serves both: rows added without ids get id = insertion position. */
+int wb_flat_create(int d, int device, wb_index** out);
+/* faiss.IndexIVFFlat(quantizer, d, nlist, METRIC_INNER_PRODUCT)   feature_search_index.py:60 */
+int wb_ivf_create(int d, int64_t nlist, int device, wb_index** out);
+int wb_free(wb_index* h);
+
+/* ---- properties: index.d / .ntotal / .is_trained / .nlist   feature_search_index.py:73,76 --- */
+int64_t wb_dim(const wb_index* h);
+int64_t wb_ntotal(const wb_index* h);
+int wb_is_trained(const wb_index* h);
+int64_t wb_nlist(const wb_index* h); /* 0 for a flat index */
+int wb_is_ivf(const wb_index* h);
+
+/* ---- build ------------------------------------------------------------------------------ */
+/* Pre-size HBM for n rows (FeatureStore.feature_count is known before the add loop,
+ * feature_search_index.py:44) so adds never re-allocate. Optional. */
+int wb_reserve(wb_index* h, int64_t n);
+/* index.add_with_ids(X, ids)   feature_search_index.py:81.  ids may be NULL (index.add).
+ * IVF: also assigns each row to its max-inner-product centroid (ties -> lowest list). */
+int wb_add_with_ids(wb_index* h, int64_t n, const float* x_host, const int64_t* ids_host);
+int wb_add_with_ids_dev(wb_index* h, int64_t n, const float* x_dev, const int64_t* ids_dev, void* stream);
+
+/* index.train(train_features)   feature_search_index.py:75  (spherical k-means, niter
+ * iterations, faiss Clustering defaults: niter=10, seed=1234).  Sets is_trained. */
+int wb_ivf_train(wb_index* h, int64_t n, const float* x_host, int niter, int64_t seed);
+/* The quantizer's centroids (what faiss keeps in index.quantizer): used to load a trained
+ * index (read_index) and to compare search on the reference's own centroids. */
+int wb_ivf_set_centroids(wb_index* h, const float* centroids_host /* [nlist*d] */);
+int wb_ivf_get_centroids(const wb_index* h, float* centroids_host /* [nlist*d] */);
+/* One k-means iteration from the current centroids over device-resident points; exposed so a
+ * sharded trainer can all-reduce sums/counts between the two halves.
+ *   assign: x -> int32 list per row, objective = sum of max inner products
+ *   accumulate: per-list fp32 sums [nlist*d] and int64 counts [nlist] of the local rows
+ *   update: centroids <- normalise(sums/counts), empty lists split (eps = 1/1024) */
+int wb_kmeans_assign_dev(wb_index* h, int64_t n, const float* x_dev, int32_t* assign_dev,
+                         double* objective_host, void* stream);
+int wb_kmeans_accumulate_dev(wb_index* h, int64_t n, const float* x_dev, const int32_t* assign_dev,
+                             float* sums_dev, int64_t* counts_dev, void* stream);
+int wb_kmeans_update_dev(wb_index* h, const float* sums_dev, const int64_t* counts_dev, int64_t n_total,
+                         int64_t seed, int64_t* nsplit_host, void* stream);
+
+/* ---- search ----------------------------------------------------------------------------- */
+/* dist, ids = index.search(x, k)   feature_search_index.py:113, api/routes.py:1407.
+ * nprobe is ignored by flat indices (index.nprobe, api/routes.py:899-902). 1 <= k <= WB_MAX_K. */
+int wb_search(wb_index* h, int64_t nq, const float* q_host, int64_t k, int64_t nprobe,
+              float* D_host, int64_t* I_host);
+int wb_search_dev(wb_index* h, int64_t nq, const float* q_dev, int64_t k, int64_t nprobe,
+                  float* D_dev, int64_t* I_dev, void* stream);
+/* Merge `nparts` sorted partial results (layout [part][nq][k], e.g. the all-gathered per-GPU
+ * top-k) into the global top-k.  Order: score desc, then part asc, then rank-in-part asc - with
+ * contiguous row sharding that is exactly "lowest insertion position". */
+int wb_merge_topk_dev(int device, int64_t nq, int64_t k, int64_t nparts, const float* D_parts_dev,
+                      const int64_t* I_parts_dev, float* D_dev, int64_t* I_dev, void* stream);
+
+/* ---- row access ------------------------------------------------------------------------- */
+/* index.reconstruct_batch(ids)   api/routes.py:1078 (after index.make_direct_map, :907).
+ * Looks rows up by external id; an unknown id is an error (faiss raises). */
+int wb_reconstruct_batch(wb_index* h, int64_t m, const int64_t* ids_host, float* out_host /* [m*d] */);
+/* Bulk export for faiss.write_index (feature_search_index.py:84): rows [start,start+n) in
+ * insertion order, their ids, and (IVF) their list assignment. Any output may be NULL. */
+int wb_export_rows(wb_index* h, int64_t start, int64_t n, float* x_host, int64_t* ids_host, int32_t* assign_host);
+/* Bulk import for faiss.read_index (feature_search_index.py:96) of an IVF index: rows with a
+ * known list assignment (no coarse quantisation is run). */
+int wb_ivf_add_preassigned(wb_index* h, int64_t n, const float* x_host, const int64_t* ids_host,
+                           const int32_t* assign_host);
+
+/* ---- introspection for bench.py / tests --------------------------------------------------- */
+/* Device pointer and row stride (floats) of the resident row store. */
+int wb_storage(wb_index* h, void** rows_dev, int64_t* ld);
+/* Number of this library's kernels launched on behalf of `h` since creation. */
+int64_t wb_launch_count(const wb_index* h);
+/* Device time (ms, CUDA events on the index's stream) of the scan kernel(s) of the last
+ * wb_search / wb_search_dev call that finished; -1 if timing was off. */
+int wb_set_timing(wb_index* h, int on);
+float wb_last_scan_ms(wb_index* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WISE_B200_H */

@@ -1,0 +1,863 @@
+// capi.cu - the C-ABI of libwiseb200.so (include/wise_b200.h): index handles, HBM row store,
+// kernel launch configuration.  Host-side plumbing only; every flop happens in scan.cuh /
+// merge.cuh / kmeans.cuh.  No CPU fallback: without a CUDA device every compute call fails.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/wise_b200.h"
+#include "kmeans.cuh"
+#include "merge.cuh"
+#include "scan.cuh"
+
+using namespace wb;
+
+// ---- errors ------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(call)              \
+    do {                       \
+        int r_ = (call);       \
+        if (r_ != 0) return r_; \
+    } while (0)
+
+extern "C" const char* wb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* wb_version(void) { return "wise_b200 0.1 (sm_100a)"; }
+extern "C" int wb_device_count(int* count) {
+    CK(cudaGetDeviceCount(count));
+    return 0;
+}
+
+// ---- grow-only device scratch --------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(bytes, (size_t)1 << 16);
+        CK(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct wb_index {
+    int device = 0;
+    int d = 0, ld = 0;
+    bool ivf = false;
+    int64_t nlist = 0;
+    bool trained = true;
+    cudaStream_t stream = nullptr;
+    // row store (insertion order)
+    float* rows = nullptr;
+    int64_t* ids = nullptr;
+    int32_t* assign = nullptr;  // IVF: list of each row
+    int64_t n = 0, cap = 0;
+    // IVF quantizer + CSR inverted lists (row indices grouped by list, insertion order kept)
+    float* centroids = nullptr;  // [nlist, ld]
+    uint32_t* perm = nullptr;
+    int64_t perm_cap = 0;
+    int64_t* list_off = nullptr;  // [nlist + 1]
+    bool csr_dirty = true;
+    // scratch
+    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff;
+    // device properties
+    int sm_count = 148;
+    int smem_max = 0;
+    // accounting
+    int64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+};
+
+static int set_dev(const wb_index* h) {
+    CK(cudaSetDevice(h->device));
+    return 0;
+}
+
+// ---- construction --------------------------------------------------------------------------
+static int create_common(int d, int device, bool ivf, int64_t nlist, wb_index** out) {
+    if (!out) return fail("out is NULL");
+    *out = nullptr;
+    if (d <= 0 || d > 65536) return fail("invalid dimension %d", d);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("no CUDA device available (%s): wise_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    wb_index* h = new wb_index();
+    h->device = device;
+    h->d = d;
+    h->ld = (d + 3) & ~3;
+    h->ivf = ivf;
+    h->nlist = nlist;
+    h->trained = !ivf;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_max = (int)prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    if (ivf) {
+        CK(cudaMalloc(&h->centroids, (size_t)nlist * h->ld * sizeof(float)));
+        CK(cudaMemsetAsync(h->centroids, 0, (size_t)nlist * h->ld * sizeof(float), h->stream));
+        CK(cudaMalloc(&h->list_off, (size_t)(nlist + 1) * sizeof(int64_t)));
+        CK(cudaMemsetAsync(h->list_off, 0, (size_t)(nlist + 1) * sizeof(int64_t), h->stream));
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int wb_flat_create(int d, int device, wb_index** out) { return create_common(d, device, false, 0, out); }
+extern "C" int wb_ivf_create(int d, int64_t nlist, int device, wb_index** out) {
+    if (nlist <= 0 || nlist > (int64_t)1 << 30) return fail("invalid nlist %lld", (long long)nlist);
+    return create_common(d, device, true, nlist, out);
+}
+
+extern "C" int wb_free(wb_index* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->rows);
+    cudaFree(h->ids);
+    cudaFree(h->assign);
+    cudaFree(h->centroids);
+    cudaFree(h->perm);
+    cudaFree(h->list_off);
+    for (DevBuf* b : {&h->parts, &h->qbuf, &h->dbuf, &h->ibuf, &h->pD, &h->pI, &h->xbuf, &h->idbuf, &h->misc,
+                      &h->kperm, &h->koff})
+        b->release();
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int64_t wb_dim(const wb_index* h) { return h ? h->d : -1; }
+extern "C" int64_t wb_ntotal(const wb_index* h) { return h ? h->n : -1; }
+extern "C" int wb_is_trained(const wb_index* h) { return h && h->trained; }
+extern "C" int64_t wb_nlist(const wb_index* h) { return h ? h->nlist : -1; }
+extern "C" int wb_is_ivf(const wb_index* h) { return h && h->ivf; }
+extern "C" int64_t wb_launch_count(const wb_index* h) { return h ? h->launches : -1; }
+extern "C" int wb_set_timing(wb_index* h, int on) {
+    if (!h) return fail("NULL index");
+    h->timing = on != 0;
+    h->ev_valid = false;
+    return 0;
+}
+extern "C" float wb_last_scan_ms(wb_index* h) {
+    if (!h || !h->ev_valid) return -1.f;
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1.f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+extern "C" int wb_storage(wb_index* h, void** rows_dev, int64_t* ld) {
+    if (!h) return fail("NULL index");
+    if (rows_dev) *rows_dev = h->rows;
+    if (ld) *ld = h->ld;
+    return 0;
+}
+
+// ---- capacity ------------------------------------------------------------------------------
+static int ensure_capacity(wb_index* h, int64_t need) {
+    if (need <= h->cap) return 0;
+    if (need >= (int64_t)0xFFFFFFFEll) return fail("an index shard is limited to 2^32-2 rows per GPU");
+    int64_t newcap = std::max<int64_t>(need, std::max<int64_t>(1024, h->cap + h->cap / 2));
+    float* nrows = nullptr;
+    int64_t* nids = nullptr;
+    int32_t* nas = nullptr;
+    CK(cudaMalloc(&nrows, (size_t)newcap * h->ld * sizeof(float)));
+    CK(cudaMalloc(&nids, (size_t)newcap * sizeof(int64_t)));
+    if (h->ivf) CK(cudaMalloc(&nas, (size_t)newcap * sizeof(int32_t)));
+    if (h->n > 0) {
+        CK(cudaMemcpyAsync(nrows, h->rows, (size_t)h->n * h->ld * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(nids, h->ids, (size_t)h->n * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream));
+        if (h->ivf)
+            CK(cudaMemcpyAsync(nas, h->assign, (size_t)h->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->rows);
+    cudaFree(h->ids);
+    cudaFree(h->assign);
+    h->rows = nrows;
+    h->ids = nids;
+    h->assign = nas;
+    h->cap = newcap;
+    return 0;
+}
+
+extern "C" int wb_reserve(wb_index* h, int64_t n) {
+    if (!h) return fail("NULL index");
+    TRY(set_dev(h));
+    return ensure_capacity(h, n);
+}
+
+// ---- scan launch ---------------------------------------------------------------------------
+struct ScanCfg {
+    int NQ, P, ck, nchunks, stages, single_copy;
+    size_t smem;
+};
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Pick queries-per-CTA, chunk width and ring depth so that everything fits the 227 KB of
+// shared memory: [ring | queries | top-k lists + queues | barriers].
+static int plan_scan(const wb_index* h, int64_t nq, int k, bool gather, int nprobe, ScanCfg* c) {
+    const int ld = h->ld;
+    int NQ = gather ? 1 : (nq >= 8 ? 8 : nq > 2 ? 4 : nq > 1 ? 2 : 1);
+    NQ = std::min(NQ, std::max(1, env_int("WB_SCAN_NQ", 8)));
+    const int P = pow2_ceil(k + kMinQueue);
+    const int ck_pref = std::max(4, env_int("WB_SCAN_CK", 256) & ~3);
+    const int max_stages = std::max(2, env_int("WB_SCAN_STAGES", 8));
+    for (; NQ >= 1; NQ >>= 1) {
+        for (int ck = std::min(ck_pref, ld); ck >= 32 || ck == ld; ck = (ck / 2) & ~3) {
+            ScanSmem L0 = scan_smem_layout(NQ, ld, P, ck, 0, gather ? nprobe : 0);
+            const size_t stage_bytes = (size_t)kGroupRows * ck * 4;
+            if (L0.total + 2 * stage_bytes + 32 > (size_t)h->smem_max) {
+                if (ck <= 32) break;
+                continue;
+            }
+            int stages = (int)std::min<size_t>(max_stages, ((size_t)h->smem_max - L0.total - 32) / (stage_bytes + 16));
+            if (stages < 2) continue;
+            c->NQ = NQ;
+            c->P = P;
+            c->ck = ck;
+            c->nchunks = (ld + ck - 1) / ck;
+            c->stages = stages;
+            c->single_copy = (!gather && c->nchunks == 1) ? 1 : 0;
+            c->smem = scan_smem_layout(NQ, ld, P, ck, stages, gather ? nprobe : 0).total;
+            return 0;
+        }
+    }
+    return fail("scan does not fit shared memory (d=%d, k=%d)", h->d, k);
+}
+
+template <int NQ, bool GATHER>
+static int launch_scan_t(const ScanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    static thread_local bool attr_done[16] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 16 && !attr_done[dev]) {
+        CK(cudaFuncSetAttribute(scan_topk_kernel<NQ, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_done[dev] = true;
+    } else if (dev >= 16) {
+        CK(cudaFuncSetAttribute(scan_topk_kernel<NQ, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    }
+    scan_topk_kernel<NQ, GATHER><<<grid, kScanThreads, smem, st>>>(p);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_scan(int NQ, bool gather, const ScanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    if (gather) return launch_scan_t<1, true>(p, grid, smem, st);
+    switch (NQ) {
+        case 1: return launch_scan_t<1, false>(p, grid, smem, st);
+        case 2: return launch_scan_t<2, false>(p, grid, smem, st);
+        case 4: return launch_scan_t<4, false>(p, grid, smem, st);
+        case 8: return launch_scan_t<8, false>(p, grid, smem, st);
+    }
+    return fail("bad NQ %d", NQ);
+}
+
+static int launch_merge_keys(wb_index* h, int64_t nq, int k, int64_t nparts, const uint64_t* keys, const int64_t* ids,
+                             float* D, int64_t* I, cudaStream_t st) {
+    MergeParams m{};
+    m.nq = nq;
+    m.k = k;
+    m.nparts = nparts;
+    const int64_t M = nparts * k;
+    m.S = std::max(pow2_ceil(2 * k), (int)std::min<int64_t>(pow2_ceil((int)std::min<int64_t>(M, 4096)), 4096));
+    m.keys = keys;
+    m.ids = ids;
+    m.D = D;
+    m.I = I;
+    merge_topk_kernel<true><<<(unsigned)nq, kMergeThreads, (size_t)m.S * 8, st>>>(m);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+// Exhaustive top-k of `nq` device queries (row stride ld) against `nrows` rows: K1 + K3.
+static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const float* q_dev, int64_t nq, int k,
+                         const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed) {
+    ScanCfg c;
+    TRY(plan_scan(h, nq, k, false, 0, &c));
+    const int64_t ngroups = (nrows + kGroupRows - 1) / kGroupRows;
+    const int64_t qgroups_total = (nq + c.NQ - 1) / c.NQ;
+    const int waves = std::max(1, env_int("WB_SCAN_WAVES", 1));
+    int64_t S = std::min<int64_t>(std::max<int64_t>(ngroups, 1),
+                                  std::max<int64_t>(1, ((int64_t)h->sm_count * waves * (qgroups_total > 1 ? 2 : 1) +
+                                                        qgroups_total - 1) / qgroups_total));
+    S = std::min<int64_t>(S, (int64_t)h->sm_count * waves);
+    TRY(h->parts.ensure((size_t)nq * S * k * sizeof(uint64_t)));
+    ScanParams p{};
+    p.rows = rows;
+    p.nrows = nrows;
+    p.ld = h->ld;
+    p.k = k;
+    p.P = c.P;
+    p.ck = c.ck;
+    p.nchunks = c.nchunks;
+    p.stages = c.stages;
+    p.single_copy = c.single_copy;
+    p.nparts = (int)S;
+    if (timed && h->timing) CK(cudaEventRecord(h->ev0, st));
+    const int64_t max_y = 32768;
+    for (int64_t g0 = 0; g0 < qgroups_total; g0 += max_y) {
+        const int64_t gy = std::min(max_y, qgroups_total - g0);
+        const int64_t qoff = g0 * c.NQ;
+        p.queries = q_dev + (size_t)qoff * h->ld;
+        p.nq = (int)std::min<int64_t>(nq - qoff, gy * c.NQ);
+        p.parts = h->parts.as<uint64_t>() + (size_t)qoff * S * k;
+        TRY(launch_scan(c.NQ, false, p, dim3((unsigned)S, (unsigned)gy), c.smem, st));
+        h->launches++;
+    }
+    if (timed && h->timing) {
+        CK(cudaEventRecord(h->ev1, st));
+        h->ev_valid = true;
+    }
+    return launch_merge_keys(h, nq, k, S, h->parts.as<uint64_t>(), ids, D, I, st);
+}
+
+// ---- CSR inverted lists (host counting sort; insertion order kept inside each list) ---------
+static int build_csr_host(const int32_t* assign_dev, int64_t n, int64_t nlist, std::vector<uint32_t>& perm,
+                          std::vector<int64_t>& off, cudaStream_t st) {
+    std::vector<int32_t> a((size_t)n);
+    if (n) CK(cudaMemcpyAsync(a.data(), assign_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    off.assign((size_t)nlist + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        if (a[i] < 0 || a[i] >= nlist) return fail("row %lld has invalid list %d", (long long)i, a[i]);
+        off[(size_t)a[i] + 1]++;
+    }
+    for (int64_t l = 0; l < nlist; ++l) off[l + 1] += off[l];
+    std::vector<int64_t> cur(off.begin(), off.end() - 1);
+    perm.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) perm[(size_t)cur[a[i]]++] = (uint32_t)i;
+    return 0;
+}
+
+static int ensure_csr(wb_index* h) {
+    if (!h->csr_dirty) return 0;
+    std::vector<uint32_t> perm;
+    std::vector<int64_t> off;
+    TRY(build_csr_host(h->assign, h->n, h->nlist, perm, off, h->stream));
+    if (h->n > h->perm_cap) {
+        cudaFree(h->perm);
+        h->perm = nullptr;
+        CK(cudaMalloc(&h->perm, (size_t)std::max<int64_t>(h->cap, h->n) * sizeof(uint32_t)));
+        h->perm_cap = std::max<int64_t>(h->cap, h->n);
+    }
+    if (h->n) CK(cudaMemcpyAsync(h->perm, perm.data(), (size_t)h->n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->list_off, off.data(), (size_t)(h->nlist + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->csr_dirty = false;
+    return 0;
+}
+
+// ---- add -----------------------------------------------------------------------------------
+// assign rows [n0, n0+n) of the store to their max-inner-product centroid (K4 with k = 1)
+static int assign_rows(wb_index* h, const float* x_dev, int64_t n, int32_t* assign_out, float* best_out,
+                       cudaStream_t st) {
+    TRY(h->pD.ensure((size_t)n * sizeof(float)));
+    TRY(h->pI.ensure((size_t)n * sizeof(int64_t)));
+    float* D = best_out ? best_out : h->pD.as<float>();
+    TRY(run_flat_scan(h, h->centroids, h->nlist, x_dev, n, 1, nullptr, D, h->pI.as<int64_t>(), st, false));
+    i64_to_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pI.as<int64_t>(), assign_out, n);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+static int add_common(wb_index* h, int64_t n, const float* x, const int64_t* ids, bool host, const int32_t* preassign,
+                      cudaStream_t st) {
+    if (!h) return fail("NULL index");
+    if (n < 0) return fail("negative n");
+    if (n == 0) return 0;
+    if (!x) return fail("x is NULL");
+    TRY(set_dev(h));
+    if (h->ivf && !h->trained) return fail("IndexIVFFlat must be trained before adding vectors");
+    TRY(ensure_capacity(h, h->n + n));
+    const int64_t n0 = h->n;
+    float* dst = h->rows + (size_t)n0 * h->ld;
+    const cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (h->ld == h->d) {
+        CK(cudaMemcpyAsync(dst, x, (size_t)n * h->d * sizeof(float), kind, st));
+    } else {
+        const float* src = x;
+        if (host) {
+            TRY(h->xbuf.ensure((size_t)n * h->d * sizeof(float)));
+            CK(cudaMemcpyAsync(h->xbuf.p, x, (size_t)n * h->d * sizeof(float), kind, st));
+            src = h->xbuf.as<float>();
+        }
+        const int64_t tot = n * h->ld;
+        pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, n, h->d, h->ld);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    if (ids) {
+        CK(cudaMemcpyAsync(h->ids + n0, ids, (size_t)n * sizeof(int64_t), kind, st));
+    } else {
+        iota_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->ids + n0, n0, n);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    if (h->ivf) {
+        if (preassign) {
+            CK(cudaMemcpyAsync(h->assign + n0, preassign, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        } else {
+            TRY(assign_rows(h, dst, n, h->assign + n0, nullptr, st));
+        }
+        h->csr_dirty = true;
+    }
+    h->n += n;
+    if (host) CK(cudaStreamSynchronize(st));  // the caller may reuse its buffers on return
+    return 0;
+}
+
+extern "C" int wb_add_with_ids(wb_index* h, int64_t n, const float* x_host, const int64_t* ids_host) {
+    return add_common(h, n, x_host, ids_host, true, nullptr, h ? h->stream : nullptr);
+}
+extern "C" int wb_add_with_ids_dev(wb_index* h, int64_t n, const float* x_dev, const int64_t* ids_dev, void* stream) {
+    return add_common(h, n, x_dev, ids_dev, false, nullptr, (cudaStream_t)stream);
+}
+extern "C" int wb_ivf_add_preassigned(wb_index* h, int64_t n, const float* x_host, const int64_t* ids_host,
+                                      const int32_t* assign_host) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    if (!assign_host) return fail("assign is NULL");
+    return add_common(h, n, x_host, ids_host, true, assign_host, h->stream);
+}
+
+// ---- search --------------------------------------------------------------------------------
+static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld] */, int64_t k, int64_t nprobe, float* D,
+                           int64_t* I, cudaStream_t st) {
+    if (!h->ivf) return run_flat_scan(h, h->rows, h->n, q_ld, nq, (int)k, h->ids, D, I, st, true);
+    if (!h->trained) return fail("IndexIVFFlat is not trained");
+    int np = (int)std::min<int64_t>(std::max<int64_t>(nprobe, 1), std::min<int64_t>(h->nlist, WB_MAX_K));
+    // K4: coarse quantizer = exhaustive scan of the centroids, top-nprobe
+    TRY(h->pD.ensure((size_t)nq * np * sizeof(float)));
+    TRY(h->pI.ensure((size_t)nq * np * sizeof(int64_t)));
+    TRY(run_flat_scan(h, h->centroids, h->nlist, q_ld, nq, np, nullptr, h->pD.as<float>(), h->pI.as<int64_t>(), st, false));
+    if (h->csr_dirty) {
+        if (st != h->stream) CK(cudaStreamSynchronize(st));
+        TRY(ensure_csr(h));
+    }
+    // K5: gather-scan of the probed lists
+    ScanCfg c;
+    TRY(plan_scan(h, 1, (int)k, true, np, &c));
+    int64_t S = nq >= h->sm_count ? 1 : std::max<int64_t>(1, (int64_t)h->sm_count / nq);
+    TRY(h->parts.ensure((size_t)nq * S * k * sizeof(uint64_t)));
+    ScanParams p{};
+    p.rows = h->rows;
+    p.nrows = 0;
+    p.ld = h->ld;
+    p.k = (int)k;
+    p.P = c.P;
+    p.ck = c.ck;
+    p.nchunks = c.nchunks;
+    p.stages = c.stages;
+    p.single_copy = 0;
+    p.nparts = (int)S;
+    p.perm = h->perm;
+    p.list_off = h->list_off;
+    p.nprobe = np;
+    if (h->timing) CK(cudaEventRecord(h->ev0, st));
+    const int64_t max_y = 32768;
+    for (int64_t q0 = 0; q0 < nq; q0 += max_y) {
+        const int64_t gy = std::min(max_y, nq - q0);
+        p.queries = q_ld + (size_t)q0 * h->ld;
+        p.nq = (int)gy;
+        p.probes = h->pI.as<int64_t>() + (size_t)q0 * np;
+        p.parts = h->parts.as<uint64_t>() + (size_t)q0 * S * k;
+        TRY(launch_scan(1, true, p, dim3((unsigned)S, (unsigned)gy), c.smem, st));
+        h->launches++;
+    }
+    if (h->timing) {
+        CK(cudaEventRecord(h->ev1, st));
+        h->ev_valid = true;
+    }
+    return launch_merge_keys(h, nq, (int)k, S, h->parts.as<uint64_t>(), h->ids, D, I, st);
+}
+
+static int check_search_args(const wb_index* h, int64_t nq, const void* q, int64_t k, const void* D, const void* I) {
+    if (!h) return fail("NULL index");
+    if (nq < 0) return fail("negative nq");
+    if (k < 1 || k > WB_MAX_K) return fail("k=%lld out of range [1, %d]", (long long)k, WB_MAX_K);
+    if (nq > 0 && (!q || !D || !I)) return fail("NULL buffer");
+    return 0;
+}
+
+// queries arrive with row stride d; the kernels want stride ld
+static int stage_queries(wb_index* h, int64_t nq, const float* q, bool host, cudaStream_t st, const float** out) {
+    if (!host && h->ld == h->d) {
+        *out = q;
+        return 0;
+    }
+    TRY(h->qbuf.ensure((size_t)nq * h->ld * sizeof(float)));
+    if (h->ld == h->d) {
+        CK(cudaMemcpyAsync(h->qbuf.p, q, (size_t)nq * h->d * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+        const float* src = q;
+        if (host) {
+            TRY(h->xbuf.ensure((size_t)nq * h->d * sizeof(float)));
+            CK(cudaMemcpyAsync(h->xbuf.p, q, (size_t)nq * h->d * sizeof(float), cudaMemcpyHostToDevice, st));
+            src = h->xbuf.as<float>();
+        }
+        const int64_t tot = nq * h->ld;
+        pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, h->qbuf.as<float>(), nq, h->d, h->ld);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    *out = h->qbuf.as<float>();
+    return 0;
+}
+
+extern "C" int wb_search_dev(wb_index* h, int64_t nq, const float* q_dev, int64_t k, int64_t nprobe, float* D_dev,
+                             int64_t* I_dev, void* stream) {
+    TRY(check_search_args(h, nq, q_dev, k, D_dev, I_dev));
+    if (nq == 0) return 0;
+    TRY(set_dev(h));
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* q = nullptr;
+    TRY(stage_queries(h, nq, q_dev, false, st, &q));
+    return search_dev_impl(h, nq, q, k, nprobe, D_dev, I_dev, st);
+}
+
+extern "C" int wb_search(wb_index* h, int64_t nq, const float* q_host, int64_t k, int64_t nprobe, float* D_host,
+                         int64_t* I_host) {
+    TRY(check_search_args(h, nq, q_host, k, D_host, I_host));
+    if (nq == 0) return 0;
+    TRY(set_dev(h));
+    cudaStream_t st = h->stream;
+    const float* q = nullptr;
+    TRY(stage_queries(h, nq, q_host, true, st, &q));
+    TRY(h->dbuf.ensure((size_t)nq * k * sizeof(float)));
+    TRY(h->ibuf.ensure((size_t)nq * k * sizeof(int64_t)));
+    TRY(search_dev_impl(h, nq, q, k, nprobe, h->dbuf.as<float>(), h->ibuf.as<int64_t>(), st));
+    CK(cudaMemcpyAsync(D_host, h->dbuf.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(I_host, h->ibuf.p, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int wb_merge_topk_dev(int device, int64_t nq, int64_t k, int64_t nparts, const float* D_parts_dev,
+                                 const int64_t* I_parts_dev, float* D_dev, int64_t* I_dev, void* stream) {
+    if (k < 1 || k > WB_MAX_K) return fail("k=%lld out of range [1, %d]", (long long)k, WB_MAX_K);
+    if (nq <= 0 || nparts <= 0) return fail("empty merge");
+    if (nparts * k >= (int64_t)0xFFFFFFFFll) return fail("too many candidates to merge");
+    CK(cudaSetDevice(device));
+    MergeParams m{};
+    m.nq = nq;
+    m.k = (int)k;
+    m.nparts = nparts;
+    const int64_t M = nparts * k;
+    m.S = std::max(pow2_ceil(2 * (int)k), (int)std::min<int64_t>(pow2_ceil((int)std::min<int64_t>(M, 4096)), 4096));
+    m.Dp = D_parts_dev;
+    m.Ip = I_parts_dev;
+    m.D = D_dev;
+    m.I = I_dev;
+    merge_topk_kernel<false><<<(unsigned)nq, kMergeThreads, (size_t)m.S * 8, (cudaStream_t)stream>>>(m);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- row access ----------------------------------------------------------------------------
+extern "C" int wb_reconstruct_batch(wb_index* h, int64_t m, const int64_t* ids_host, float* out_host) {
+    if (!h) return fail("NULL index");
+    if (m < 0) return fail("negative m");
+    if (m == 0) return 0;
+    if (!ids_host || !out_host) return fail("NULL buffer");
+    TRY(set_dev(h));
+    cudaStream_t st = h->stream;
+    TRY(h->idbuf.ensure((size_t)m * 2 * sizeof(int64_t)));
+    TRY(h->xbuf.ensure((size_t)m * h->d * sizeof(float)));
+    int64_t* tgt = h->idbuf.as<int64_t>();
+    unsigned long long* pos = reinterpret_cast<unsigned long long*>(tgt + m);
+    CK(cudaMemcpyAsync(tgt, ids_host, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(pos, 0xFF, (size_t)m * sizeof(int64_t), st));
+    for (int64_t j0 = 0; j0 < m; j0 += 64) {
+        const int mm = (int)std::min<int64_t>(64, m - j0);
+        const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>((h->n + 255) / 256, 1), h->sm_count * 8);
+        find_ids_kernel<<<grid, 256, 0, st>>>(h->ids, h->n, tgt + j0, mm, pos + j0);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    std::vector<int64_t> hpos((size_t)m);
+    CK(cudaMemcpyAsync(hpos.data(), pos, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int64_t j = 0; j < m; ++j)
+        if (hpos[j] < 0) return fail("reconstruct: id %lld not found in the index", (long long)ids_host[j]);
+    const int64_t tot = m * h->d;
+    gather_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->rows, h->ld, h->d, (const int64_t*)pos, m,
+                                                                       h->xbuf.as<float>());
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaMemcpyAsync(out_host, h->xbuf.p, (size_t)tot * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int wb_export_rows(wb_index* h, int64_t start, int64_t n, float* x_host, int64_t* ids_host,
+                              int32_t* assign_host) {
+    if (!h) return fail("NULL index");
+    if (start < 0 || n < 0 || start + n > h->n) return fail("export range [%lld,%lld) outside [0,%lld)",
+                                                            (long long)start, (long long)(start + n), (long long)h->n);
+    if (n == 0) return 0;
+    TRY(set_dev(h));
+    cudaStream_t st = h->stream;
+    if (x_host)
+        CK(cudaMemcpy2DAsync(x_host, (size_t)h->d * 4, h->rows + (size_t)start * h->ld, (size_t)h->ld * 4,
+                             (size_t)h->d * 4, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (ids_host) CK(cudaMemcpyAsync(ids_host, h->ids + start, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (assign_host) {
+        if (!h->ivf) return fail("assignments exist only for IVF indices");
+        CK(cudaMemcpyAsync(assign_host, h->assign + start, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- IVF quantizer / k-means -----------------------------------------------------------------
+extern "C" int wb_ivf_set_centroids(wb_index* h, const float* c) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    if (!c) return fail("NULL centroids");
+    if (h->n > 0) return fail("cannot replace the centroids of a non-empty index");
+    TRY(set_dev(h));
+    CK(cudaMemsetAsync(h->centroids, 0, (size_t)h->nlist * h->ld * 4, h->stream));
+    CK(cudaMemcpy2DAsync(h->centroids, (size_t)h->ld * 4, c, (size_t)h->d * 4, (size_t)h->d * 4, (size_t)h->nlist,
+                         cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->trained = true;
+    return 0;
+}
+
+extern "C" int wb_ivf_get_centroids(const wb_index* h, float* c) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    if (!c) return fail("NULL centroids");
+    TRY(set_dev(h));
+    CK(cudaMemcpy2DAsync(c, (size_t)h->d * 4, h->centroids, (size_t)h->ld * 4, (size_t)h->d * 4, (size_t)h->nlist,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// x_dev has row stride d; kernels need stride ld
+static int stage_points(wb_index* h, int64_t n, const float* x_dev, cudaStream_t st, const float** out) {
+    if (h->ld == h->d) {
+        *out = x_dev;
+        return 0;
+    }
+    TRY(h->xbuf.ensure((size_t)n * h->ld * sizeof(float)));
+    const int64_t tot = n * h->ld;
+    pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x_dev, h->xbuf.as<float>(), n, h->d, h->ld);
+    CK(cudaGetLastError());
+    h->launches++;
+    *out = h->xbuf.as<float>();
+    return 0;
+}
+
+extern "C" int wb_kmeans_assign_dev(wb_index* h, int64_t n, const float* x_dev, int32_t* assign_dev,
+                                    double* objective_host, void* stream) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    if (n <= 0 || !x_dev || !assign_dev) return fail("bad arguments");
+    TRY(set_dev(h));
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* x = nullptr;
+    TRY(stage_points(h, n, x_dev, st, &x));
+    TRY(h->dbuf.ensure((size_t)n * sizeof(float)));
+    TRY(assign_rows(h, x, n, assign_dev, h->dbuf.as<float>(), st));
+    if (objective_host) {
+        TRY(h->misc.ensure(sizeof(double)));
+        CK(cudaMemsetAsync(h->misc.p, 0, sizeof(double), st));
+        sum_f32_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, st>>>(h->dbuf.as<float>(), n,
+                                                                                          h->misc.as<double>());
+        CK(cudaGetLastError());
+        h->launches++;
+        CK(cudaMemcpyAsync(objective_host, h->misc.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+extern "C" int wb_kmeans_accumulate_dev(wb_index* h, int64_t n, const float* x_dev, const int32_t* assign_dev,
+                                        float* sums_dev, int64_t* counts_dev, void* stream) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    if (n < 0 || !sums_dev || !counts_dev) return fail("bad arguments");
+    TRY(set_dev(h));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<uint32_t> perm;
+    std::vector<int64_t> off;
+    TRY(build_csr_host(assign_dev, n, h->nlist, perm, off, st));
+    TRY(h->kperm.ensure(std::max<size_t>((size_t)n * 4, 16)));
+    TRY(h->koff.ensure((size_t)(h->nlist + 1) * 8));
+    if (n) CK(cudaMemcpyAsync(h->kperm.p, perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->koff.p, off.data(), (size_t)(h->nlist + 1) * 8, cudaMemcpyHostToDevice, st));
+    segment_sum_kernel<<<(unsigned)h->nlist, 256, 0, st>>>(x_dev, h->d, h->d, h->kperm.as<uint32_t>(),
+                                                          h->koff.as<int64_t>(), sums_dev, counts_dev);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaStreamSynchronize(st));  // perm/off host vectors die here
+    return 0;
+}
+
+extern "C" int wb_kmeans_update_dev(wb_index* h, const float* sums_dev, const int64_t* counts_dev, int64_t n_total,
+                                    int64_t seed, int64_t* nsplit_host, void* stream) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    TRY(set_dev(h));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t k = h->nlist;
+    const int d = h->d, ld = h->ld;
+    const int64_t tot = k * d;
+    centroid_mean_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(sums_dev, counts_dev, h->centroids, ld, d, k);
+    CK(cudaGetLastError());
+    h->launches++;
+    // split_clusters [faiss-upstream]: an empty list takes a perturbed copy of a list picked with
+    // probability ~ its size; eps = 1/1024.  Host logic on the (small) centroid table.
+    std::vector<int64_t> cnt((size_t)k);
+    CK(cudaMemcpyAsync(cnt.data(), counts_dev, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int64_t nsplit = 0;
+    bool any_empty = false;
+    for (int64_t c = 0; c < k; ++c) any_empty |= cnt[c] == 0;
+    if (any_empty && n_total > k) {
+        std::vector<float> cen((size_t)k * ld);
+        CK(cudaMemcpyAsync(cen.data(), h->centroids, (size_t)k * ld * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        std::mt19937 mt((uint32_t)seed);
+        std::vector<double> hass(cnt.begin(), cnt.end());
+        const float EPS = 1.0f / 1024.0f;
+        for (int64_t ci = 0; ci < k; ++ci) {
+            if (hass[ci] != 0) continue;
+            int64_t cj = 0;
+            for (int64_t guard = 0;; cj = (cj + 1) % k) {
+                const float p = (float)((hass[cj] - 1.0) / (double)(n_total - k));
+                const float r = (float)mt() / (float)mt.max();
+                if (r < p) break;
+                if (++guard > k * 1000) return fail("split_clusters did not converge");
+            }
+            float* a = &cen[(size_t)ci * ld];
+            float* b = &cen[(size_t)cj * ld];
+            for (int j = 0; j < d; ++j) {
+                a[j] = b[j];
+                if (j % 2 == 0) {
+                    a[j] *= 1 + EPS;
+                    b[j] *= 1 - EPS;
+                } else {
+                    a[j] *= 1 - EPS;
+                    b[j] *= 1 + EPS;
+                }
+            }
+            hass[ci] = (double)((int64_t)hass[cj] / 2);
+            hass[cj] -= hass[ci];
+            nsplit++;
+        }
+        CK(cudaMemcpyAsync(h->centroids, cen.data(), (size_t)k * ld * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    renorm_rows_kernel<<<(unsigned)k, 256, 0, st>>>(h->centroids, ld, d);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (nsplit_host) *nsplit_host = nsplit;
+    return 0;
+}
+
+extern "C" int wb_ivf_train(wb_index* h, int64_t n, const float* x_host, int niter, int64_t seed) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    if (h->n > 0) return fail("cannot train a non-empty index");
+    if (n < h->nlist) return fail("Number of training points (%lld) should be at least as large as number of clusters (%lld)",
+                                   (long long)n, (long long)h->nlist);
+    if (!x_host) return fail("NULL training set");
+    TRY(set_dev(h));
+    cudaStream_t st = h->stream;
+    const int64_t k = h->nlist;
+    const int d = h->d;
+    float* x = nullptr;
+    CK(cudaMalloc(&x, (size_t)n * d * 4));
+    int rc = 0;
+    int32_t* assign = nullptr;
+    float* sums = nullptr;
+    int64_t* counts = nullptr;
+    do {
+        if ((rc = (cudaMemcpyAsync(x, x_host, (size_t)n * d * 4, cudaMemcpyHostToDevice, st) != cudaSuccess))) break;
+        if ((rc = (cudaMalloc(&assign, (size_t)n * 4) != cudaSuccess))) break;
+        if ((rc = (cudaMalloc(&sums, (size_t)k * d * 4) != cudaSuccess))) break;
+        if ((rc = (cudaMalloc(&counts, (size_t)k * 8) != cudaSuccess))) break;
+        // initial centroids: first k rows of the faiss-style random permutation, seed + 1
+        std::mt19937 mt((uint32_t)(seed + 1));
+        std::vector<int64_t> perm((size_t)n);
+        for (int64_t i = 0; i < n; ++i) perm[i] = i;
+        for (int64_t i = 0; i + 1 < n; ++i) {
+            const int64_t i2 = i + (int64_t)(mt() % (uint64_t)(n - i));
+            std::swap(perm[i], perm[i2]);
+        }
+        if ((rc = (cudaMemsetAsync(h->centroids, 0, (size_t)k * h->ld * 4, st) != cudaSuccess))) break;
+        for (int64_t c = 0; c < k && !rc; ++c)
+            rc = cudaMemcpyAsync(h->centroids + (size_t)c * h->ld, x + (size_t)perm[c] * d, (size_t)d * 4,
+                                 cudaMemcpyDeviceToDevice, st) != cudaSuccess;
+        if (rc) break;
+        renorm_rows_kernel<<<(unsigned)k, 256, 0, st>>>(h->centroids, h->ld, d);
+        h->launches++;
+        for (int it = 0; it < niter && !rc; ++it) {
+            double obj = 0;
+            if ((rc = wb_kmeans_assign_dev(h, n, x, assign, &obj, st))) break;
+            if ((rc = wb_kmeans_accumulate_dev(h, n, x, assign, sums, counts, st))) break;
+            int64_t nsplit = 0;
+            if ((rc = wb_kmeans_update_dev(h, sums, counts, n, 1234, &nsplit, st))) break;
+        }
+    } while (0);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(x);
+    cudaFree(assign);
+    cudaFree(sums);
+    cudaFree(counts);
+    if (rc) {
+        if (g_err.empty()) fail("k-means training failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    if (e != cudaSuccess) return fail("k-means training failed: %s", cudaGetErrorString(e));
+    h->trained = true;
+    return 0;
+}

@@ -1,0 +1,134 @@
+// common.cuh - PTX helpers (mbarrier, bulk async copy, named barriers) and the sortable
+// (score, position) key shared by every selection kernel.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wb {
+
+constexpr int kWarp = 32;
+
+// ---- sortable 64-bit key ---------------------------------------------------------------
+// key = orderable(score) << 32 | ~position.  Larger key == better candidate: higher score
+// first, then LOWER position (the tie rule).  key 0 is "empty".
+__device__ __forceinline__ uint32_t order_f32(float f) {
+    f += 0.0f;  // -0.0 -> +0.0
+    uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float unorder_f32(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t pos) {
+    return ((uint64_t)order_f32(score) << 32) | (uint64_t)(0xFFFFFFFFu - pos);
+}
+__device__ __forceinline__ float key_score(uint64_t k) { return unorder_f32((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_pos(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)k; }
+
+// ---- shared-memory addresses -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier ----------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// Spin on a phase parity.  A bounded spin turns a protocol bug into a trap (launch failure)
+// instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    const uint32_t a = smem_u32(bar);
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+
+// ---- 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP) ------------------------
+// dst/src 16-byte aligned, bytes a multiple of 16; completion is signalled on `bar` as
+// complete_tx(bytes).
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- named barriers (sub-CTA sync among the consumer warps) -----------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// barrier + OR-reduction of a per-thread predicate; every participant gets the result.
+__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
+    uint32_t out;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 q, %1, 0;\n"
+        "bar.red.or.pred p, %2, %3, q;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(out)
+        : "r"((uint32_t)pred), "r"(id), "r"(nthreads)
+        : "memory");
+    return out != 0;
+}
+
+__host__ __device__ __forceinline__ int pow2_ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// ---- bitonic sort of `nlists` arrays of P (power of two) keys, descending -------------------
+// Executed by NT threads that share barrier `bar_id` (bar_id < 0 => __syncthreads()).
+template <int NT>
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int P, int nlists, int tid, int bar_id) {
+    const int half = P >> 1;
+    const int total = nlists * half;
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < total; i += NT) {
+                const int l = i / half;
+                const int j = i - l * half;
+                const int pos = 2 * j - (j & (stride - 1));
+                uint64_t* base = keys + (size_t)l * P;
+                const uint64_t a = base[pos], b = base[pos + stride];
+                const bool desc = ((pos & size) == 0);
+                if ((a < b) == desc) {
+                    base[pos] = b;
+                    base[pos + stride] = a;
+                }
+            }
+            if (bar_id < 0) __syncthreads();
+            else named_bar_sync(bar_id, NT);
+        }
+    }
+}
+
+}  // namespace wb

@@ -1,0 +1,77 @@
+// kmeans.cuh - K7 kmeans_update: deterministic per-list sums, mean, spherical renormalisation.
+// Replaces faiss Clustering::train's compute_centroids + post_process_centroids
+// [faiss-upstream], reached from index.train(), /root/reference/src/index/feature_search_index.py:75.
+// (K6, the assignment, is scan_topk_kernel with k = 1 over the centroids.)
+// HBM-bound: n*d*4 bytes read once, nlist*d*4 written.  No float atomics: each list is summed
+// by one CTA in insertion order, so training is bit-reproducible.
+#pragma once
+#include "common.cuh"
+
+namespace wb {
+
+// sums[c, 0:d] = sum over slots of list c of x[perm[slot], 0:d]; counts[c] = list size
+__global__ void __launch_bounds__(256) segment_sum_kernel(const float* x, int ldx, int d, const uint32_t* perm,
+                                                          const int64_t* off, float* sums, int64_t* counts) {
+    const int64_t c = blockIdx.x;
+    const int64_t b = off[c], e = off[c + 1];
+    if (threadIdx.x == 0) counts[c] = e - b;
+    for (int col = threadIdx.x; col < d; col += blockDim.x) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // fixed 4-way interleave: order is static
+        int64_t s = b;
+        for (; s + 4 <= e; s += 4) {
+            a0 += x[(size_t)perm[s] * ldx + col];
+            a1 += x[(size_t)perm[s + 1] * ldx + col];
+            a2 += x[(size_t)perm[s + 2] * ldx + col];
+            a3 += x[(size_t)perm[s + 3] * ldx + col];
+        }
+        for (; s < e; ++s) a0 += x[(size_t)perm[s] * ldx + col];
+        sums[c * d + col] = (a0 + a1) + (a2 + a3);
+    }
+}
+
+// centroid <- sums / count for non-empty lists (empty lists keep their centroid)
+__global__ void centroid_mean_kernel(const float* sums, const int64_t* counts, float* cent, int ld, int d,
+                                     int64_t nlist) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nlist * d) {
+        const int64_t c = i / d;
+        const int col = (int)(i - c * d);
+        const int64_t n = counts[c];
+        if (n > 0) cent[c * ld + col] = sums[i] / (float)n;
+    }
+}
+
+// spherical k-means: L2-normalise each centroid row (fvec_renorm_L2); zero rows stay zero
+__global__ void __launch_bounds__(256) renorm_rows_kernel(float* cent, int ld, int d) {
+    __shared__ float red[8];
+    float* row = cent + (size_t)blockIdx.x * ld;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) s += row[c] * row[c];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    if (t > 0.f) {
+        const float inv = 1.0f / sqrtf(t);
+        for (int c = threadIdx.x; c < d; c += blockDim.x) row[c] *= inv;
+    }
+}
+
+// out += sum(v[0:n]) in double (objective of one k-means iteration)
+__global__ void __launch_bounds__(256) sum_f32_kernel(const float* v, int64_t n, double* out) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += (double)v[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(out, t);
+    }
+}
+
+}  // namespace wb

@@ -1,0 +1,125 @@
+// merge.cuh - K3 topk_merge: merge per-CTA (or per-GPU) partial top-k lists into the final
+// (D, I) rows.  Replaces faiss heap_reorder / HeapResultHandler::end and the parallel_mode-1
+// merge of IndexIVF::search [faiss-upstream]; runs inside every index.search()
+// (/root/reference/src/index/feature_search_index.py:113, /root/reference/api/routes.py:1407).
+// Latency-bound: one CTA per query, bitonic sort in shared memory over rounds of candidates.
+#pragma once
+#include <float.h>
+#include "common.cuh"
+
+namespace wb {
+
+constexpr int kMergeThreads = 1024;
+
+struct MergeParams {
+    int64_t nq;
+    int k;
+    int64_t nparts;
+    int S;  // sort buffer entries (power of two, >= 2k)
+    // source A: keys [nq][nparts][k] from scan_topk_kernel; positions -> ids via ids/id_base
+    const uint64_t* keys;
+    const int64_t* ids;  // may be null: id = position
+    // source B: (D, I) parts [nparts][nq][k] (multi-GPU merge)
+    const float* Dp;
+    const int64_t* Ip;
+    float* D;    // [nq][k]
+    int64_t* I;  // [nq][k]
+};
+
+template <bool FROM_KEYS>
+__global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_merge[];
+    unsigned char* smem = smem_merge;
+    uint64_t* buf = reinterpret_cast<uint64_t*>(smem);
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    const int k = p.k, S = p.S;
+    const int64_t M = p.nparts * (int64_t)k;
+    int keep = 0;
+    for (int64_t next = 0; next < M || keep == 0;) {
+        const int room = S - keep;
+        const int take = (int)min((int64_t)room, M - next);
+        for (int i = tid; i < room; i += kMergeThreads) {
+            uint64_t key = 0ull;
+            if (i < take) {
+                const int64_t c = next + i;
+                if constexpr (FROM_KEYS) {
+                    key = p.keys[q * M + c];
+                } else {
+                    const int64_t part = c / k, slot = c - part * k;
+                    const int64_t src = (part * p.nq + q) * k + slot;
+                    if (p.Ip[src] >= 0) key = make_key(p.Dp[src], (uint32_t)c);
+                }
+            }
+            buf[keep + i] = key;
+        }
+        __syncthreads();
+        bitonic_sort_desc<kMergeThreads>(buf, S, 1, tid, -1);
+        next += take;
+        keep = k;
+        if (take == 0) break;
+    }
+    for (int j = tid; j < k; j += kMergeThreads) {
+        const uint64_t key = buf[j];
+        float d = -FLT_MAX;
+        int64_t id = -1;
+        if (key) {
+            d = key_score(key);
+            const uint32_t pos = key_pos(key);
+            if constexpr (FROM_KEYS) {
+                id = p.ids ? p.ids[pos] : (int64_t)pos;
+            } else {
+                const int64_t part = pos / k, slot = pos - part * k;
+                id = p.Ip[(part * p.nq + q) * k + slot];
+            }
+        }
+        p.D[q * k + j] = d;
+        p.I[q * k + j] = id;
+    }
+}
+
+// ---- small utility kernels ---------------------------------------------------------------
+__global__ void iota_ids_kernel(int64_t* ids, int64_t start, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = start + i;
+}
+
+__global__ void i64_to_i32_kernel(const int64_t* in, int32_t* out, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)in[i];
+}
+
+// dst[n, ld] <- src[n, d], zero padding columns d..ld
+__global__ void pad_rows_kernel(const float* src, float* dst, int64_t n, int d, int ld) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n * ld) {
+        const int64_t r = i / ld;
+        const int c = (int)(i - r * ld);
+        dst[i] = c < d ? src[r * d + c] : 0.f;
+    }
+}
+
+// out[m, d] <- rows[pos[m], 0:d]
+__global__ void gather_rows_kernel(const float* rows, int ld, int d, const int64_t* pos, int64_t m, float* out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < m * d) {
+        const int64_t r = i / d;
+        const int c = (int)(i - r * d);
+        out[i] = rows[(size_t)pos[r] * ld + c];
+    }
+}
+
+// pos[j] = lowest position whose id equals targets[j] (-1 if none); m <= 64 per launch
+__global__ void find_ids_kernel(const int64_t* ids, int64_t n, const int64_t* targets, int m,
+                                unsigned long long* pos) {
+    __shared__ int64_t t[64];
+    if (threadIdx.x < m) t[threadIdx.x] = targets[threadIdx.x];
+    __syncthreads();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = ids[i];
+        for (int j = 0; j < m; ++j)
+            if (v == t[j]) atomicMin(&pos[j], (unsigned long long)i);
+    }
+}
+
+}  // namespace wb

@@ -1,0 +1,309 @@
+// scan.cuh - K1 flat_scan_topk and K5 ivf_list_scan_topk (one kernel, two row sources).
+//
+// Replaces faiss knn_inner_product/exhaustive_inner_product_seq + heap (IndexFlat::search) and
+// IndexIVF::search_preassigned + IVFFlatScanner::scan_codes [faiss-upstream], reached from
+// /root/reference/src/index/feature_search_index.py:113 and /root/reference/api/routes.py:1407.
+//
+// HBM-bound streaming kernel (DESIGN.md "K1"):
+//   * one persistent CTA per SM: warp 0 is the producer, warps 1..8 are consumers;
+//   * the producer streams "row groups" of 32 rows through a ring of shared-memory stages with
+//     1-D bulk async copies (cp.async.bulk -> UBLKCP, the TMA engine), one copy per row chunk,
+//     completion on an mbarrier (full[]); consumers hand stages back through empty[];
+//   * each consumer warp owns 4 rows of the group and NQ (1/2/4/8) queries: 128-bit LDS of the
+//     row chunk and of the query chunk (queries are resident in shared memory), FMA into 4*NQ
+//     register accumulators, then a transposing warp-shuffle reduction that leaves each
+//     (row, query) score in one lane;
+//   * fused top-k: a score survives only if it beats the CTA's current k-th best for that query
+//     (register compare against a shared threshold); survivors go to a small shared-memory
+//     queue; when a queue fills, the consumers bitonic-sort [top-k list | queue] in shared
+//     memory and tighten the threshold.  Scores never go to HBM; each CTA writes k keys per
+//     query at the end, merged by merge_topk_kernel (merge.cuh).
+// Algorithmic bytes per launch: nrows * ld * 4 (the row store is read exactly once per pass).
+#pragma once
+#include "common.cuh"
+
+namespace wb {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kRowsPerWarp = 4;
+constexpr int kGroupRows = kConsumerWarps * kRowsPerWarp;  // 32
+constexpr int kConsumerThreads = kConsumerWarps * kWarp;   // 256
+constexpr int kScanThreads = kConsumerThreads + kWarp;     // 288
+constexpr int kBarConsumers = 1;
+constexpr int kMinQueue = 64;  // queue capacity >= 2 * kGroupRows
+
+struct ScanParams {
+    const float* rows;      // row store [*, ld]
+    int64_t nrows;          // flat: rows to scan; gather: unused
+    int ld;                 // row stride in floats (multiple of 4)
+    const float* queries;   // [nq, ld]
+    int nq;
+    int k;
+    int P;                  // per-query list size (power of two >= k + kMinQueue)
+    int ck;                 // chunk width in floats (multiple of 4)
+    int nchunks;            // ceil(ld / ck)
+    int stages;
+    int single_copy;        // flat && nchunks == 1: one bulk copy per group
+    uint64_t* parts;        // [nq][nparts][k] keys
+    int nparts;             // == gridDim.x
+    // gather mode (IVF): candidates = concatenation of the probed lists of query blockIdx.y
+    const uint32_t* perm;     // CSR: row index per slot
+    const int64_t* list_off;  // CSR: [nlist + 1]
+    const int64_t* probes;    // [nq][nprobe] list ids (-1 = none)
+    int nprobe;
+};
+
+struct ScanSmem {
+    size_t ring, queries, lists, bars, misc, prefix, total;
+};
+
+__host__ __device__ inline ScanSmem scan_smem_layout(int NQ, int ld, int P, int ck, int stages, int nprobe) {
+    ScanSmem L;
+    size_t o = 0;
+    L.ring = o;    o += (size_t)stages * kGroupRows * ck * 4;
+    L.queries = o; o += (size_t)NQ * ld * 4;
+    o = (o + 15) & ~(size_t)15;
+    L.lists = o;   o += (size_t)NQ * P * 8;
+    L.bars = o;    o += (size_t)stages * 2 * 8;
+    L.misc = o;    o += (size_t)NQ * 8;  // qcnt[NQ] (int) + thr_s[NQ] (float)
+    L.prefix = o;  o += nprobe > 0 ? (size_t)(nprobe + 1) * 4 + (size_t)nprobe * 4 : 0;
+    L.total = (o + 15) & ~(size_t)15;
+    return L;
+}
+
+// Sum V per-lane partials across the warp, V in {4,8,16,32}.  Returns the total of value
+// index (lane >> (5 - log2 V)) - every lane of that index group holds the same sum.
+template <int N, int OFF>
+__device__ __forceinline__ void multi_reduce_step(float* v, int lane) {
+    if constexpr (OFF >= 1) {
+        if constexpr (N > 1) {
+            constexpr int H = N / 2;
+            const bool up = (lane & OFF) != 0;
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                const float keep = up ? v[i + H] : v[i];
+                const float send = up ? v[i] : v[i + H];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+            }
+            multi_reduce_step<H, OFF / 2>(v, lane);
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
+            multi_reduce_step<1, OFF / 2>(v, lane);
+        }
+    }
+}
+
+template <int V>
+struct Log2 { static constexpr int value = 1 + Log2<V / 2>::value; };
+template <>
+struct Log2<1> { static constexpr int value = 0; };
+
+struct GatherCtx {
+    const uint32_t* prefix;  // smem [nprobe + 1] exclusive prefix of probed list sizes
+    const int* plist;        // smem [nprobe]
+    const uint32_t* perm;
+    const int64_t* list_off;
+    int nprobe;
+};
+
+__device__ __forceinline__ uint32_t gather_row(const GatherCtx& G, uint32_t cpos) {
+    int lo = 0, hi = G.nprobe - 1;  // largest j with prefix[j] <= cpos
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (G.prefix[mid] <= cpos) lo = mid;
+        else hi = mid - 1;
+    }
+    const int64_t slot = G.list_off[G.plist[lo]] + (int64_t)(cpos - G.prefix[lo]);
+    return G.perm[slot];
+}
+
+template <int NQ, bool GATHER>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanParams p) {
+    extern __shared__ __align__(128) unsigned char smem_scan[];
+    unsigned char* smem = smem_scan;
+    const ScanSmem L = scan_smem_layout(NQ, p.ld, p.P, p.ck, p.stages, GATHER ? p.nprobe : 0);
+    float* ring = reinterpret_cast<float*>(smem + L.ring);
+    float* qs = reinterpret_cast<float*>(smem + L.queries);
+    uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.lists);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* empty = full + p.stages;
+    int* qcnt = reinterpret_cast<int*>(smem + L.misc);
+    float* thr_s = reinterpret_cast<float*>(smem + L.misc) + NQ;
+    uint32_t* prefix = reinterpret_cast<uint32_t*>(smem + L.prefix);
+    int* plist = reinterpret_cast<int*>(prefix + (GATHER ? p.nprobe + 1 : 0));
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.y * NQ;
+    const int nqv = min(NQ, p.nq - q0);
+    const int ld = p.ld, d4 = ld >> 2, ck = p.ck, ck4 = ck >> 2;
+    const int k = p.k, P = p.P;
+    const int qcap = P - k;
+    const int hw_mark = qcap - kGroupRows;
+
+    // ---- prologue: barriers, queries, empty lists ------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < NQ * d4; i += kScanThreads) {
+        const int b = i / d4, c = i - b * d4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < nqv) v = reinterpret_cast<const float4*>(p.queries + (size_t)(q0 + b) * ld)[c];
+        reinterpret_cast<float4*>(qs)[i] = v;
+    }
+    for (int i = tid; i < NQ * P; i += kScanThreads) lists[i] = 0ull;
+    if (tid < NQ) {
+        qcnt[tid] = 0;
+        thr_s[tid] = tid < nqv ? -INFINITY : INFINITY;
+    }
+    int64_t total = p.nrows;
+    GatherCtx G{prefix, plist, p.perm, p.list_off, p.nprobe};
+    if constexpr (GATHER) {
+        if (warp == 0) {  // exclusive prefix sum of the probed list sizes
+            uint32_t carry = 0;
+            for (int base = 0; base < p.nprobe; base += 32) {
+                const int j = base + lane;
+                uint32_t sz = 0;
+                int l = 0;
+                if (j < p.nprobe) {
+                    const int64_t lid = p.probes[(size_t)blockIdx.y * p.nprobe + j];
+                    if (lid >= 0) {
+                        l = (int)lid;
+                        sz = (uint32_t)(p.list_off[lid + 1] - p.list_off[lid]);
+                    }
+                    plist[j] = l;
+                }
+                uint32_t inc = sz;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (j < p.nprobe) prefix[j] = carry + inc - sz;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) prefix[p.nprobe] = carry;
+        }
+    }
+    __syncthreads();
+    if constexpr (GATHER) total = prefix[p.nprobe];
+    const int64_t ngroups = (total + kGroupRows - 1) / kGroupRows;
+    const size_t stage_floats = (size_t)kGroupRows * ck;
+
+    if (warp == 0) {
+        // ================================ producer ==========================================
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+            const int64_t p0 = g * kGroupRows;
+            const int nvalid = (int)min((int64_t)kGroupRows, total - p0);
+            const float* src = nullptr;
+            if (lane < nvalid) {
+                const int64_t row = GATHER ? (int64_t)gather_row(G, (uint32_t)(p0 + lane)) : p0 + lane;
+                src = p.rows + (size_t)row * ld;
+            }
+            for (int ch = 0; ch < p.nchunks; ++ch) {
+                if (lane == 0) mbar_wait(&empty[s], ph ^ 1u);
+                __syncwarp();
+                const int cfl = min(ck, ld - ch * ck);
+                const uint32_t cbytes = (uint32_t)cfl * 4u;
+                if (lane == 0) mbar_arrive_expect_tx(&full[s], cbytes * (uint32_t)nvalid);
+                __syncwarp();
+                float* dst = ring + (size_t)s * stage_floats;
+                if (!GATHER && p.single_copy) {
+                    if (lane == 0) bulk_g2s(dst, src, cbytes * (uint32_t)nvalid, &full[s]);
+                } else if (lane < nvalid) {
+                    bulk_g2s(dst + (size_t)lane * ck, src + (size_t)ch * ck, cbytes, &full[s]);
+                }
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        // ================================ consumers =========================================
+        const int cw = warp - 1;
+        const int ctid = tid - kWarp;
+        constexpr int V = kRowsPerWarp * NQ;
+        constexpr int LV = Log2<V>::value;
+        const float4* q4 = reinterpret_cast<const float4*>(qs);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+            float acc[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[i] = 0.f;
+            for (int ch = 0; ch < p.nchunks; ++ch) {
+                mbar_wait(&full[s], ph);
+                const float4* tile =
+                    reinterpret_cast<const float4*>(ring + (size_t)s * stage_floats) + (size_t)(cw * kRowsPerWarp) * ck4;
+                const int c4n = min(ck4, d4 - ch * ck4);
+                const float4* qb = q4 + ch * ck4;
+#pragma unroll 2
+                for (int i = lane; i < c4n; i += 32) {
+                    float4 x[kRowsPerWarp];
+#pragma unroll
+                    for (int r = 0; r < kRowsPerWarp; ++r) x[r] = tile[r * ck4 + i];
+#pragma unroll
+                    for (int b = 0; b < NQ; ++b) {
+                        const float4 q = qb[b * d4 + i];
+#pragma unroll
+                        for (int r = 0; r < kRowsPerWarp; ++r) {
+                            float a = acc[r * NQ + b];
+                            a = fmaf(x[r].x, q.x, a);
+                            a = fmaf(x[r].y, q.y, a);
+                            a = fmaf(x[r].z, q.z, a);
+                            a = fmaf(x[r].w, q.w, a);
+                            acc[r * NQ + b] = a;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+            multi_reduce_step<V, 16>(acc, lane);
+            const float score = acc[0];
+            const int vi = lane >> (5 - LV);
+            const bool owner = (lane & ((32 >> LV) - 1)) == 0;
+            const int r = vi / NQ, b = vi % NQ;
+            bool hw = false;
+            if (owner) {
+                const int64_t cpos = g * kGroupRows + cw * kRowsPerWarp + r;
+                if (cpos < total && score >= thr_s[b]) {
+                    const uint32_t pos = GATHER ? gather_row(G, (uint32_t)cpos) : (uint32_t)cpos;
+                    const uint64_t key = make_key(score, pos);
+                    if (key > lists[(size_t)b * P + k - 1]) {
+                        const int slot = atomicAdd(&qcnt[b], 1);
+                        lists[(size_t)b * P + k + slot] = key;
+                        hw = slot + 1 > hw_mark;
+                    }
+                }
+            }
+            if (named_bar_or(kBarConsumers, kConsumerThreads, hw)) {
+                bitonic_sort_desc<kConsumerThreads>(lists, P, nqv, ctid, kBarConsumers);
+                for (int i = ctid; i < nqv * qcap; i += kConsumerThreads) {
+                    const int l = i / qcap, j = i - l * qcap;
+                    lists[(size_t)l * P + k + j] = 0ull;
+                }
+                if (ctid < nqv) {
+                    qcnt[ctid] = 0;
+                    const uint64_t t = lists[(size_t)ctid * P + k - 1];
+                    thr_s[ctid] = t ? key_score(t) : -INFINITY;
+                }
+                named_bar_sync(kBarConsumers, kConsumerThreads);
+            }
+        }
+        // ---- epilogue: final sort, k best keys of this CTA for each query -------------------
+        named_bar_sync(kBarConsumers, kConsumerThreads);
+        bitonic_sort_desc<kConsumerThreads>(lists, P, nqv, ctid, kBarConsumers);
+        for (int i = ctid; i < nqv * k; i += kConsumerThreads) {
+            const int l = i / k, j = i - l * k;
+            p.parts[((size_t)(q0 + l) * p.nparts + blockIdx.x) * k + j] = lists[(size_t)l * P + j];
+        }
+    }
+}
+
+}  // namespace wb

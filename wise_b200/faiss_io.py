@@ -1,0 +1,284 @@
+"""Reader / writer for the `.faiss` index files WISE keeps on disk
+(`<index_dir>/<media_type>-<IndexType>.faiss`, /root/reference/src/index/feature_search_index.py:30-31,84,96).
+
+Byte layout restated from upstream faiss `impl/index_write.cpp` / `index_read.cpp`
+[faiss-upstream; no faiss build is available in this image to cross-check - SURVEY.md 8f-2]:
+
+  header(idx)  = int32 d | int64 ntotal | int64 1<<20 | int64 1<<20 | uint8 is_trained | int32 metric_type
+  IndexFlatIP  = "IxFI" header  uint64 nfloats  float32[nfloats]
+  IndexIDMap   = "IxMp" header  <nested index>  uint64 n  int64[n]
+  IndexIVFFlat = "IwFl" header  uint64 nlist  uint64 nprobe  <nested quantizer>
+                 direct_map{uint8 type | uint64 n | int64[n]}
+                 "ilar" uint64 nlist  uint64 code_size
+                 ("full" uint64 nlist  uint64 sizes[nlist]  |  "sprs" uint64 2m  (list, size)[m])
+                 then for every non-empty list: codes uint8[n*code_size]  ids int64[n]
+
+Rows stream between the file and HBM in bounded chunks, so an index larger than host RAM
+can be written or read.
+"""
+from __future__ import annotations
+
+import os
+import struct
+
+import numpy as np
+
+from . import _capi
+from . import faiss_compat as fc
+
+_CHUNK_ROWS = 1 << 16
+_DUMMY = 1 << 20
+
+
+def _hdr(f, d: int, ntotal: int, is_trained: bool, metric: int) -> None:
+    f.write(struct.pack("<iqqqBi", d, ntotal, _DUMMY, _DUMMY, 1 if is_trained else 0, metric))
+
+
+def _read_hdr(f):
+    d, ntotal, _, _, trained, metric = struct.unpack("<iqqqBi", _need(f, 4 + 8 * 3 + 1 + 4))
+    if metric > 1:
+        _need(f, 4)  # metric_arg
+    return d, ntotal, bool(trained), metric
+
+
+def _need(f, n: int) -> bytes:
+    b = f.read(n)
+    if len(b) != n:
+        raise RuntimeError(f"read error in index file: wanted {n} bytes, got {len(b)}")  # faiss READANDCHECK
+    return b
+
+
+def _write_flat(f, index, centroids: np.ndarray | None = None) -> None:
+    """IxFI block for an IndexFlatIP (or for an IVF quantizer given its centroid table)."""
+    f.write(b"IxFI")
+    if centroids is not None:
+        n, d = centroids.shape
+        _hdr(f, d, n, True, fc.METRIC_INNER_PRODUCT)
+        f.write(struct.pack("<Q", n * d))
+        f.write(np.ascontiguousarray(centroids, np.float32).tobytes())
+        return
+    n, d = index.ntotal, index.d
+    _hdr(f, d, n, True, fc.METRIC_INNER_PRODUCT)
+    f.write(struct.pack("<Q", n * d))
+    for s in range(0, n, _CHUNK_ROWS):
+        x, _, _ = index._export(s, min(_CHUNK_ROWS, n - s))
+        f.write(x.tobytes())
+
+
+def write_index(index, fname: str) -> None:
+    tmp = f"{fname}.tmp.{os.getpid()}"
+    with open(tmp, "wb") as f:
+        if isinstance(index, fc.IndexIDMap):
+            n = index.ntotal
+            f.write(b"IxMp")
+            _hdr(f, index.d, n, True, fc.METRIC_INNER_PRODUCT)
+            _write_flat(f, index)
+            f.write(struct.pack("<Q", n))
+            for s in range(0, n, _CHUNK_ROWS):
+                _, ids, _ = index._export(s, min(_CHUNK_ROWS, n - s))
+                f.write(ids.tobytes())
+        elif isinstance(index, fc.IndexFlatIP):
+            _write_flat(f, index)
+        elif isinstance(index, fc.IndexIVFFlat):
+            _write_ivf(f, index)
+        else:
+            raise RuntimeError(f"don't know how to serialize this type of index: {type(index).__name__}")
+    os.replace(tmp, fname)  # atomic: an index file either exists completely or not at all
+
+
+def _write_ivf(f, index) -> None:
+    n, d, nlist = index.ntotal, index.d, index.nlist
+    f.write(b"IwFl")
+    _hdr(f, d, n, index.is_trained, fc.METRIC_INNER_PRODUCT)
+    f.write(struct.pack("<QQ", nlist, int(index.nprobe)))
+    _write_flat(f, None, index.centroids() if index.is_trained else np.zeros((0, d), np.float32))
+    # direct map: only the type byte and an (empty or sequential) array
+    dm_type = index.direct_map.type
+    f.write(struct.pack("<B", dm_type))
+    # list membership
+    assign = np.empty((n,), np.int32)
+    ids = np.empty((n,), np.int64)
+    for s in range(0, n, 1 << 20):
+        m = min(1 << 20, n - s)
+        _capi.check(_capi.lib().wb_export_rows(index._h, s, m, None, _capi.ptr(ids[s:s + m]), _capi.ptr(assign[s:s + m])))
+    order = np.argsort(assign, kind="stable")  # CSR: rows of each list in insertion order
+    sizes = np.bincount(assign, minlength=nlist).astype(np.uint64)
+    if dm_type == fc.DirectMap.Array:
+        # lo_build(list, offset) = list << 32 | offset, indexed by id (ids are 0..n-1 here)
+        off_in_list = np.empty(n, np.int64)
+        starts = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+        off_in_list[order] = np.arange(n, dtype=np.int64) - starts[assign[order]]
+        arr = np.full(n, -1, np.int64)
+        arr[ids] = (assign.astype(np.int64) << 32) | off_in_list
+        f.write(struct.pack("<Q", n))
+        f.write(arr.tobytes())
+    else:
+        f.write(struct.pack("<Q", 0))
+    f.write(b"ilar")
+    f.write(struct.pack("<QQ", nlist, d * 4))
+    non0 = int((sizes > 0).sum())
+    if non0 > nlist // 2:
+        f.write(b"full")
+        f.write(struct.pack("<Q", nlist))
+        f.write(sizes.tobytes())
+    else:
+        f.write(b"sprs")
+        nz = np.nonzero(sizes)[0].astype(np.uint64)
+        pairs = np.stack([nz, sizes[nz]], axis=1).reshape(-1)
+        f.write(struct.pack("<Q", pairs.size))
+        f.write(pairs.tobytes())
+    pos = 0
+    for l in range(nlist):
+        m = int(sizes[l])
+        if m == 0:
+            continue
+        rows = order[pos:pos + m]
+        pos += m
+        for s in range(0, m, _CHUNK_ROWS):
+            f.write(_gather_rows(index, rows[s:s + _CHUNK_ROWS]).tobytes())
+        f.write(ids[rows].tobytes())
+
+
+def _gather_rows(index, rows: np.ndarray) -> np.ndarray:
+    """Rows by insertion position (contiguous runs are exported in one call)."""
+    out = np.empty((rows.size, index.d), np.float32)
+    if rows.size == 0:
+        return out
+    breaks = np.nonzero(np.diff(rows) != 1)[0] + 1
+    starts = np.concatenate([[0], breaks])
+    ends = np.concatenate([breaks, [rows.size]])
+    for s, e in zip(starts, ends):
+        x, _, _ = index._export(int(rows[s]), int(e - s))
+        out[s:e] = x
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def read_index(fname: str, io_flags: int = 0):
+    with open(fname, "rb") as f:
+        return _read_any(f)
+
+
+def _read_flat_body(f, add_rows) -> tuple[int, int]:
+    d, ntotal, _, metric = _read_hdr(f)
+    if metric != fc.METRIC_INNER_PRODUCT:
+        raise RuntimeError("wise_b200 reads METRIC_INNER_PRODUCT indices only")
+    (nfl,) = struct.unpack("<Q", _need(f, 8))
+    if nfl != ntotal * d:
+        raise RuntimeError(f"corrupt IndexFlat block: {nfl} floats for {ntotal} x {d}")
+    add_rows(d, ntotal)
+    return d, ntotal
+
+
+def _stream_rows(f, d: int, n: int, sink) -> None:
+    for s in range(0, n, _CHUNK_ROWS):
+        m = min(_CHUNK_ROWS, n - s)
+        x = np.frombuffer(_need(f, m * d * 4), np.float32).reshape(m, d)
+        sink(s, x)
+
+
+def _read_any(f):
+    tag = _need(f, 4)
+    if tag == b"IxFI":
+        box = {}
+
+        def add_rows(d, n):
+            idx = fc.IndexFlatIP(d)
+            idx.reserve(n)
+            _stream_rows(f, d, n, lambda s, x: idx.add(x))
+            box["i"] = idx
+
+        _read_flat_body(f, add_rows)
+        return box["i"]
+    if tag == b"IxMp":
+        d, ntotal, _, _ = _read_hdr(f)
+        sub = _need(f, 4)
+        if sub != b"IxFI":
+            raise RuntimeError(f"IndexIDMap over {sub!r} is not supported (WISE wraps IndexFlatIP)")
+        # rows come before ids in the file: stage rows with provisional ids, then rewrite the ids
+        flat = fc.IndexFlatIP(d)
+        idmap = fc.IndexIDMap(flat)
+        hdr_d, n, _, _ = _read_hdr(f)
+        (nfl,) = struct.unpack("<Q", _need(f, 8))
+        if hdr_d != d or nfl != n * d:
+            raise RuntimeError("corrupt IndexIDMap block")
+        rows_at = f.tell()
+        f.seek(rows_at + n * d * 4)
+        (nid,) = struct.unpack("<Q", _need(f, 8))
+        if nid != n:
+            raise RuntimeError("corrupt IndexIDMap block: id_map size mismatch")
+        ids_at = f.tell()
+        idmap.reserve(n)
+        for s in range(0, n, _CHUNK_ROWS):
+            m = min(_CHUNK_ROWS, n - s)
+            f.seek(rows_at + s * d * 4)
+            x = np.frombuffer(_need(f, m * d * 4), np.float32).reshape(m, d)
+            f.seek(ids_at + s * 8)
+            ids = np.frombuffer(_need(f, m * 8), np.int64)
+            idmap.add_with_ids(x, ids)
+        return idmap
+    if tag == b"IwFl":
+        return _read_ivf(f)
+    raise RuntimeError(f"Index type {tag!r} not recognized")  # faiss message shape
+
+
+def _read_ivf(f):
+    d, ntotal, trained, metric = _read_hdr(f)
+    if metric != fc.METRIC_INNER_PRODUCT:
+        raise RuntimeError("wise_b200 reads METRIC_INNER_PRODUCT indices only")
+    nlist, nprobe = struct.unpack("<QQ", _need(f, 16))
+    qtag = _need(f, 4)
+    if qtag != b"IxFI":
+        raise RuntimeError(f"IVF quantizer {qtag!r} is not supported (WISE uses IndexFlatIP)")
+    qd, qn, _, _ = _read_hdr(f)
+    (nfl,) = struct.unpack("<Q", _need(f, 8))
+    cent = np.frombuffer(_need(f, nfl * 4), np.float32).reshape(qn, qd) if nfl else np.zeros((0, d), np.float32)
+    quant = fc.IndexFlatIP(d)
+    index = fc.IndexIVFFlat(quant, d, int(nlist), fc.METRIC_INNER_PRODUCT)
+    index.nprobe = int(nprobe)
+    if trained:
+        if qn != nlist:
+            raise RuntimeError("corrupt IVF block: quantizer size != nlist")
+        index.set_centroids(cent.copy())
+    (dm_type,) = struct.unpack("<B", _need(f, 1))
+    (dm_n,) = struct.unpack("<Q", _need(f, 8))
+    f.seek(dm_n * 8, os.SEEK_CUR)
+    if dm_type == fc.DirectMap.Hashtable:
+        (hn,) = struct.unpack("<Q", _need(f, 8))
+        f.seek(hn * 16, os.SEEK_CUR)
+    if _need(f, 4) != b"ilar":
+        raise RuntimeError("only ArrayInvertedLists ('ilar') are supported")
+    il_nlist, code_size = struct.unpack("<QQ", _need(f, 16))
+    if il_nlist != nlist or code_size != d * 4:
+        raise RuntimeError("corrupt inverted lists header")
+    ltype = _need(f, 4)
+    (nsz,) = struct.unpack("<Q", _need(f, 8))
+    raw = np.frombuffer(_need(f, nsz * 8), np.uint64)
+    sizes = np.zeros(nlist, np.int64)
+    if ltype == b"full":
+        sizes[:] = raw.astype(np.int64)
+    elif ltype == b"sprs":
+        sizes[raw[0::2].astype(np.int64)] = raw[1::2].astype(np.int64)
+    else:
+        raise RuntimeError(f"unknown inverted list encoding {ltype!r}")
+    index.reserve(int(sizes.sum()))
+    for l in range(int(nlist)):
+        m = int(sizes[l])
+        if m == 0:
+            continue
+        codes_at = f.tell()
+        ids_at = codes_at + m * d * 4
+        f.seek(ids_at)
+        ids = np.frombuffer(_need(f, m * 8), np.int64)
+        end = f.tell()
+        for s in range(0, m, _CHUNK_ROWS):
+            mm = min(_CHUNK_ROWS, m - s)
+            f.seek(codes_at + s * d * 4)
+            x = np.frombuffer(_need(f, mm * d * 4), np.float32).reshape(mm, d)
+            a = np.full(mm, l, np.int32)
+            _capi.check(_capi.lib().wb_ivf_add_preassigned(index._h, mm, _capi.ptr(x), _capi.ptr(np.ascontiguousarray(ids[s:s + mm])),
+                                                           _capi.ptr(a)))
+        f.seek(end)
+    if dm_type == fc.DirectMap.Array:
+        index.direct_map.type = fc.DirectMap.Array
+    return index
