@@ -233,7 +233,7 @@ extern "C" int wb_reserve(wb_index* h, int64_t n) {
 
 // ---- scan launch ---------------------------------------------------------------------------
 struct ScanCfg {
-    int NQ, P, ck, nchunks, stages, single_copy;
+    int NQ, RW, P, ck, nchunks, stages, single_copy;
     size_t smem;
 };
 
@@ -242,63 +242,89 @@ static int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-// Pick queries-per-CTA, chunk width and ring depth so that everything fits the 227 KB of
+// Pick queries-per-CTA, rows-per-warp and ring depth so that everything fits the 227 KB of
 // shared memory: [ring | queries | top-k lists + queues | barriers].
+// Measured on B200 (profiles/r01_scan_sweep.md): one bulk copy engine request costs the producer
+// ~27 cycles, so stages hold WHOLE rows - a flat row group is then one contiguous copy (7.2 TB/s);
+// chunked stages (one 1 KB copy per row and chunk) top out at 4.0 TB/s and are only the fallback
+// for rows too wide for two whole-row stages.
 static int plan_scan(const wb_index* h, int64_t nq, int k, bool gather, int nprobe, ScanCfg* c) {
     const int ld = h->ld;
     int NQ = gather ? 1 : (nq >= 8 ? 8 : nq > 2 ? 4 : nq > 1 ? 2 : 1);
     NQ = std::min(NQ, std::max(1, env_int("WB_SCAN_NQ", 8)));
     const int P = pow2_ceil(k + kMinQueue);
-    const int ck_pref = std::max(4, env_int("WB_SCAN_CK", 256) & ~3);
     const int max_stages = std::max(2, env_int("WB_SCAN_STAGES", 8));
+    const int rw_max = std::min(4, std::max(1, env_int("WB_SCAN_RW", 4)));
+    const int ck_env = env_int("WB_SCAN_CK", 0) & ~3;
+    const int np = gather ? nprobe : 0;
     for (; NQ >= 1; NQ >>= 1) {
-        for (int ck = std::min(ck_pref, ld); ck >= 32 || ck == ld; ck = (ck / 2) & ~3) {
-            ScanSmem L0 = scan_smem_layout(NQ, ld, P, ck, 0, gather ? nprobe : 0);
-            const size_t stage_bytes = (size_t)kGroupRows * ck * 4;
-            if (L0.total + 2 * stage_bytes + 32 > (size_t)h->smem_max) {
-                if (ck <= 32) break;
-                continue;
+        if (ck_env == 0 || ck_env >= ld) {
+            for (int RW = rw_max; RW >= 1; RW >>= 1) {  // whole-row stages
+                const int gr = kConsumerWarps * RW;
+                const size_t fixed = scan_smem_layout(NQ, ld, P, ld, 0, np, gr).total;
+                const size_t stage_bytes = (size_t)gr * ld * 4;
+                if (fixed + 2 * stage_bytes + 64 > (size_t)h->smem_max) continue;
+                if (stage_bytes >= (1u << 20)) continue;  // mbarrier tx-count limit
+                const int stages = (int)std::min<size_t>(max_stages, ((size_t)h->smem_max - fixed - 64) / (stage_bytes + 16));
+                *c = ScanCfg{NQ, RW, P, ld, 1, stages, gather ? 0 : 1, 0};
+                c->smem = scan_smem_layout(NQ, ld, P, ld, stages, np, gr).total;
+                return 0;
             }
-            int stages = (int)std::min<size_t>(max_stages, ((size_t)h->smem_max - L0.total - 32) / (stage_bytes + 16));
-            if (stages < 2) continue;
-            c->NQ = NQ;
-            c->P = P;
-            c->ck = ck;
-            c->nchunks = (ld + ck - 1) / ck;
-            c->stages = stages;
-            c->single_copy = (!gather && c->nchunks == 1) ? 1 : 0;
-            c->smem = scan_smem_layout(NQ, ld, P, ck, stages, gather ? nprobe : 0).total;
+        }
+        const int RW = rw_max;  // chunked fallback: very wide rows
+        const int gr = kConsumerWarps * RW;
+        for (int ck = std::min(ck_env ? ck_env : 1024, ld) & ~3; ck >= 32; ck = (ck / 2) & ~3) {
+            const size_t fixed = scan_smem_layout(NQ, ld, P, ck, 0, np, gr).total;
+            const size_t stage_bytes = (size_t)gr * ck * 4;
+            if (fixed + 2 * stage_bytes + 64 > (size_t)h->smem_max) continue;
+            const int stages = (int)std::min<size_t>(max_stages, ((size_t)h->smem_max - fixed - 64) / (stage_bytes + 16));
+            *c = ScanCfg{NQ, RW, P, ck, (ld + ck - 1) / ck, stages, 0, 0};
+            c->smem = scan_smem_layout(NQ, ld, P, ck, stages, np, gr).total;
             return 0;
         }
     }
     return fail("scan does not fit shared memory (d=%d, k=%d)", h->d, k);
 }
 
-template <int NQ, bool GATHER>
+template <int NQ, int RW, bool GATHER>
 static int launch_scan_t(const ScanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-    static thread_local bool attr_done[16] = {};
+    static thread_local bool attr_done[64] = {};
     int dev = 0;
     CK(cudaGetDevice(&dev));
-    if (dev < 16 && !attr_done[dev]) {
-        CK(cudaFuncSetAttribute(scan_topk_kernel<NQ, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        attr_done[dev] = true;
-    } else if (dev >= 16) {
-        CK(cudaFuncSetAttribute(scan_topk_kernel<NQ, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    if (dev >= 64 || !attr_done[dev]) {
+        CK(cudaFuncSetAttribute(scan_topk_kernel<NQ, RW, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        if (dev < 64) attr_done[dev] = true;
     }
-    scan_topk_kernel<NQ, GATHER><<<grid, kScanThreads, smem, st>>>(p);
+    scan_topk_kernel<NQ, RW, GATHER><<<grid, kScanThreads, smem, st>>>(p);
     CK(cudaGetLastError());
     return 0;
 }
 
-static int launch_scan(int NQ, bool gather, const ScanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-    if (gather) return launch_scan_t<1, true>(p, grid, smem, st);
-    switch (NQ) {
-        case 1: return launch_scan_t<1, false>(p, grid, smem, st);
-        case 2: return launch_scan_t<2, false>(p, grid, smem, st);
-        case 4: return launch_scan_t<4, false>(p, grid, smem, st);
-        case 8: return launch_scan_t<8, false>(p, grid, smem, st);
+template <int NQ, bool GATHER>
+static int launch_scan_rw(int RW, const ScanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    switch (RW) {
+        case 4: return launch_scan_t<NQ, 4, GATHER>(p, grid, smem, st);
+        case 2: return launch_scan_t<NQ, 2, GATHER>(p, grid, smem, st);
+        case 1: return launch_scan_t<NQ, 1, GATHER>(p, grid, smem, st);
     }
-    return fail("bad NQ %d", NQ);
+    return fail("bad RW %d", RW);
+}
+
+static int launch_scan(const ScanCfg& c, bool gather, ScanParams& p, dim3 grid, cudaStream_t st) {
+    p.P = c.P;
+    p.ck = c.ck;
+    p.nchunks = c.nchunks;
+    p.stages = c.stages;
+    p.single_copy = c.single_copy;
+    p.rw = c.RW;
+    if (gather) return launch_scan_rw<1, true>(c.RW, p, grid, c.smem, st);
+    switch (c.NQ) {
+        case 1: return launch_scan_rw<1, false>(c.RW, p, grid, c.smem, st);
+        case 2: return launch_scan_rw<2, false>(c.RW, p, grid, c.smem, st);
+        case 4: return launch_scan_rw<4, false>(c.RW, p, grid, c.smem, st);
+        case 8: return launch_scan_rw<8, false>(c.RW, p, grid, c.smem, st);
+    }
+    return fail("bad NQ %d", c.NQ);
 }
 
 static int launch_merge_keys(wb_index* h, int64_t nq, int k, int64_t nparts, const uint64_t* keys, const int64_t* ids,
@@ -324,7 +350,8 @@ static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const fl
                          const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed) {
     ScanCfg c;
     TRY(plan_scan(h, nq, k, false, 0, &c));
-    const int64_t ngroups = (nrows + kGroupRows - 1) / kGroupRows;
+    const int gr = kConsumerWarps * c.RW;
+    const int64_t ngroups = (nrows + gr - 1) / gr;
     const int64_t qgroups_total = (nq + c.NQ - 1) / c.NQ;
     const int waves = std::max(1, env_int("WB_SCAN_WAVES", 1));
     int64_t S = std::min<int64_t>(std::max<int64_t>(ngroups, 1),
@@ -337,11 +364,6 @@ static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const fl
     p.nrows = nrows;
     p.ld = h->ld;
     p.k = k;
-    p.P = c.P;
-    p.ck = c.ck;
-    p.nchunks = c.nchunks;
-    p.stages = c.stages;
-    p.single_copy = c.single_copy;
     p.nparts = (int)S;
     if (timed && h->timing) CK(cudaEventRecord(h->ev0, st));
     const int64_t max_y = 32768;
@@ -351,7 +373,7 @@ static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const fl
         p.queries = q_dev + (size_t)qoff * h->ld;
         p.nq = (int)std::min<int64_t>(nq - qoff, gy * c.NQ);
         p.parts = h->parts.as<uint64_t>() + (size_t)qoff * S * k;
-        TRY(launch_scan(c.NQ, false, p, dim3((unsigned)S, (unsigned)gy), c.smem, st));
+        TRY(launch_scan(c, false, p, dim3((unsigned)S, (unsigned)gy), st));
         h->launches++;
     }
     if (timed && h->timing) {
@@ -495,11 +517,6 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
     p.nrows = 0;
     p.ld = h->ld;
     p.k = (int)k;
-    p.P = c.P;
-    p.ck = c.ck;
-    p.nchunks = c.nchunks;
-    p.stages = c.stages;
-    p.single_copy = 0;
     p.nparts = (int)S;
     p.perm = h->perm;
     p.list_off = h->list_off;
@@ -512,7 +529,7 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
         p.nq = (int)gy;
         p.probes = h->pI.as<int64_t>() + (size_t)q0 * np;
         p.parts = h->parts.as<uint64_t>() + (size_t)q0 * S * k;
-        TRY(launch_scan(1, true, p, dim3((unsigned)S, (unsigned)gy), c.smem, st));
+        TRY(launch_scan(c, true, p, dim3((unsigned)S, (unsigned)gy), st));
         h->launches++;
     }
     if (h->timing) {

@@ -25,12 +25,12 @@
 namespace wb {
 
 constexpr int kConsumerWarps = 8;
-constexpr int kRowsPerWarp = 4;
-constexpr int kGroupRows = kConsumerWarps * kRowsPerWarp;  // 32
+constexpr int kMaxRowsPerWarp = 4;
+constexpr int kMaxGroupRows = kConsumerWarps * kMaxRowsPerWarp;  // 32
 constexpr int kConsumerThreads = kConsumerWarps * kWarp;   // 256
 constexpr int kScanThreads = kConsumerThreads + kWarp;     // 288
 constexpr int kBarConsumers = 1;
-constexpr int kMinQueue = 64;  // queue capacity >= 2 * kGroupRows
+constexpr int kMinQueue = 64;  // queue capacity >= 2 * kMaxGroupRows
 
 struct ScanParams {
     const float* rows;      // row store [*, ld]
@@ -44,6 +44,7 @@ struct ScanParams {
     int nchunks;            // ceil(ld / ck)
     int stages;
     int single_copy;        // flat && nchunks == 1: one bulk copy per group
+    int rw;                 // rows per consumer warp (4, 2 or 1); a row group is 8 * rw rows
     uint64_t* parts;        // [nq][nparts][k] keys
     int nparts;             // == gridDim.x
     // gather mode (IVF): candidates = concatenation of the probed lists of query blockIdx.y
@@ -57,10 +58,11 @@ struct ScanSmem {
     size_t ring, queries, lists, bars, misc, prefix, total;
 };
 
-__host__ __device__ inline ScanSmem scan_smem_layout(int NQ, int ld, int P, int ck, int stages, int nprobe) {
+__host__ __device__ inline ScanSmem scan_smem_layout(int NQ, int ld, int P, int ck, int stages, int nprobe,
+                                                     int group_rows) {
     ScanSmem L;
     size_t o = 0;
-    L.ring = o;    o += (size_t)stages * kGroupRows * ck * 4;
+    L.ring = o;    o += (size_t)stages * group_rows * ck * 4;
     L.queries = o; o += (size_t)NQ * ld * 4;
     o = (o + 15) & ~(size_t)15;
     L.lists = o;   o += (size_t)NQ * P * 8;
@@ -117,11 +119,13 @@ __device__ __forceinline__ uint32_t gather_row(const GatherCtx& G, uint32_t cpos
     return G.perm[slot];
 }
 
-template <int NQ, bool GATHER>
+template <int NQ, int RW, bool GATHER>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanParams p) {
+    constexpr int kRowsPerWarp = RW;
+    constexpr int kGroupRows = kConsumerWarps * RW;
     extern __shared__ __align__(128) unsigned char smem_scan[];
     unsigned char* smem = smem_scan;
-    const ScanSmem L = scan_smem_layout(NQ, p.ld, p.P, p.ck, p.stages, GATHER ? p.nprobe : 0);
+    const ScanSmem L = scan_smem_layout(NQ, p.ld, p.P, p.ck, p.stages, GATHER ? p.nprobe : 0, kGroupRows);
     float* ring = reinterpret_cast<float*>(smem + L.ring);
     float* qs = reinterpret_cast<float*>(smem + L.queries);
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.lists);
