@@ -1,0 +1,227 @@
+"""GPU parity tests for IndexFlatIP / IndexIDMap: CUDA path (through the C-ABI) vs the CPU oracle.
+Tolerances (BASELINE.json north_star): scores within 1e-5 absolute of the fp64-accumulated oracle;
+id lists identical outside near-tie bands of 2e-6 (oracle.compare_topk), ties -> lowest position."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def faiss():
+    from wise_b200 import faiss_compat
+    return faiss_compat
+
+
+def _flat(faiss, xb, ids=None):
+    if ids is None:
+        idx = faiss.IndexFlatIP(xb.shape[1])
+        idx.add(xb)
+    else:
+        idx = faiss.IndexIDMap(faiss.IndexFlatIP(xb.shape[1]))
+        idx.add_with_ids(xb, ids)
+    return idx
+
+
+def test_golden_fixture(faiss):
+    g = np.load(os.path.join(GOLD, "flat_small.npz"))
+    idx = _flat(faiss, g["xb"], g["ids"])
+    D, I = idx.search(g["xq"], int(g["k"]))
+    r = O.compare_topk(D, I, g["D"], g["I"])
+    assert r["rows"] == 4
+    # exact duplicate rows 5 / 205 have bit-identical scores on the GPU too: lowest position first
+    assert I[3, 0] == 5 * 7 + 3 and I[3, 1] == 205 * 7 + 3 and D[3, 0] == D[3, 1]
+
+
+def test_config1_100k_x_512_16q_top10(faiss):
+    """BASELINE config[0] in full."""
+    xb = O.unit_gaussian(100000, 512, 1234)
+    xq = O.unit_gaussian(16, 512, 4321)
+    idx = _flat(faiss, xb)
+    assert idx.ntotal == 100000 and idx.d == 512 and idx.is_trained
+    D, I = idx.search(xq, 10)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (16, 10)
+    Dr, Ir = O.flat_search(xb, xq, 10)
+    r = O.compare_topk(D, I, Dr, Ir)
+    assert r["exact_rows"] >= 15, r
+
+
+def test_config1_with_one_percent_duplicates(faiss):
+    xb = O.unit_gaussian(100000, 512, 1234)
+    xb[50000:51000] = xb[:1000]
+    xq = np.concatenate([O.unit_gaussian(12, 512, 4321), xb[10:14]])
+    ids = np.arange(100000, dtype=np.int64) * 2 + 1
+    idx = _flat(faiss, xb, ids)
+    D, I = idx.search(xq, 10)
+    Dr, Ir = O.flat_search(xb, xq, 10, ids)
+    O.compare_topk(D, I, Dr, Ir)
+    for j in range(4):  # a query equal to a duplicated row: the two copies tie exactly, lowest position wins
+        assert I[12 + j, 0] == ids[10 + j] and I[12 + j, 1] == ids[50010 + j]
+
+
+@pytest.mark.parametrize("n,d,nq,k", [
+    (1, 4, 1, 1), (5, 64, 2, 10), (31, 8, 3, 4), (33, 12, 1, 40), (1000, 64, 1, 5), (20000, 100, 5, 7),
+    (20000, 30, 9, 2048), (33333, 1024, 3, 1000), (50000, 768, 8, 100), (40000, 1536, 2, 10),
+    (3000, 4096, 4, 16), (100000, 512, 40, 1), (70000, 768, 1, 100), (25000, 2048, 7, 33)])
+def test_shapes(faiss, n, d, nq, k):
+    xb = O.unit_gaussian(n, d, n + d)
+    xq = O.unit_gaussian(nq, d, nq + k)
+    idx = _flat(faiss, xb)
+    D, I = idx.search(xq, k)
+    Dr, Ir = O.flat_search(xb, xq, k)
+    O.compare_topk(D, I, Dr, Ir)
+    if k > n:
+        assert np.all(I[:, n:] == -1) and np.all(D[:, n:] == O.NEG_FLT_MAX)
+
+
+def test_clustered_clip_like_data_top100(faiss):
+    xb = O.clustered_unit(200000, 768, 512, 2024)
+    xq = O.clustered_unit(8, 768, 512, 2025)
+    idx = _flat(faiss, xb)
+    D, I = idx.search(xq, 100)
+    Dr, Ir = O.flat_search(xb, xq, 100)
+    O.compare_topk(D, I, Dr, Ir)
+    D1, I1 = idx.search(xq[:1], 100)  # n=1 (the API's case) takes a different kernel instance
+    O.compare_topk(D1, I1, Dr[:1], Ir[:1])
+
+
+def test_empty_index_and_incremental_adds(faiss):
+    idx = faiss.IndexIDMap(faiss.IndexFlatIP(32))
+    xq = O.unit_gaussian(2, 32, 1)
+    D, I = idx.search(xq, 5)
+    assert np.all(I == -1) and np.all(D == O.NEG_FLT_MAX)
+    xb = O.unit_gaussian(3000, 32, 2)
+    ids = np.arange(3000, dtype=np.int64)[::-1].copy() + 10
+    for s in range(0, 3000, 512):  # the reference adds in 512-row batches (feature_search_index.py:79-82)
+        idx.add_with_ids(xb[s:s + 512], ids[s:s + 512])
+    assert idx.ntotal == 3000
+    D, I = idx.search(xq, 5)
+    O.compare_topk(D, I, *O.flat_search(xb, xq, 5, ids))
+
+
+def test_api_surface_and_errors(faiss):
+    flat = faiss.IndexFlatIP(16)
+    assert not hasattr(flat, "nprobe") and not hasattr(flat, "direct_map")  # api/routes.py:899,1317 use hasattr
+    with pytest.raises(RuntimeError):
+        flat.add_with_ids(O.unit_gaussian(2, 16, 0), np.array([1, 2]))
+    idm = faiss.IndexIDMap(flat)
+    assert not hasattr(idm, "nprobe") and not hasattr(idm, "direct_map")
+    with pytest.raises(TypeError):
+        idm.search(np.zeros((1, 16), np.float64), 3)
+    with pytest.raises(AssertionError):
+        idm.search(np.zeros((1, 8), np.float32), 3)
+    with pytest.raises(RuntimeError):
+        idm.search(np.zeros((1, 16), np.float32), 5000)  # k > WB_MAX_K
+    flat2 = faiss.IndexFlatIP(16)
+    flat2.add(O.unit_gaussian(4, 16, 0))
+    with pytest.raises(RuntimeError):
+        faiss.IndexIDMap(flat2)  # "index must be empty on input"
+
+
+def test_device_pointer_api_and_merge(faiss):
+    """wb_search_dev / wb_add_with_ids_dev / wb_merge_topk_dev with torch-owned device memory."""
+    import torch
+    from wise_b200 import _capi
+    L = _capi.lib()
+    n, d, nq, k = 60000, 256, 5, 50
+    xb = O.unit_gaussian(n, d, 3)
+    xq = O.unit_gaussian(nq, d, 4)
+    Dr, Ir = O.flat_search(xb, xq, k)
+    st = torch.cuda.current_stream().cuda_stream
+    parts_D, parts_I = [], []
+    bounds = [0, 20000, 20001, 45000, n]
+    xd = torch.from_numpy(xb).cuda()
+    qd = torch.from_numpy(xq).cuda()
+    for a, b in zip(bounds[:-1], bounds[1:]):  # 4 "ranks" holding contiguous row ranges
+        idx = faiss.IndexFlatIP(d)
+        ids = torch.arange(a, b, dtype=torch.int64, device="cuda")
+        _capi.check(L.wb_add_with_ids_dev(idx._h, b - a, xd[a:b].contiguous().data_ptr(), ids.data_ptr(), st))
+        D = torch.empty(nq, k, device="cuda")
+        I = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+        _capi.check(L.wb_search_dev(idx._h, nq, qd.data_ptr(), k, 1, D.data_ptr(), I.data_ptr(), st))
+        torch.cuda.synchronize()
+        parts_D.append(D); parts_I.append(I)
+    Dp = torch.stack(parts_D).contiguous(); Ip = torch.stack(parts_I).contiguous()
+    Dm = torch.empty(nq, k, device="cuda"); Im = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+    _capi.check(L.wb_merge_topk_dev(0, nq, k, 4, Dp.data_ptr(), Ip.data_ptr(), Dm.data_ptr(), Im.data_ptr(), st))
+    torch.cuda.synchronize()
+    O.compare_topk(Dm.cpu().numpy(), Im.cpu().numpy(), Dr, Ir)
+    # the single-row shard returns k-1 padded slots; merged result must not contain them
+    assert (Ip[1, :, 1:] == -1).all() and (Im >= 0).all()
+
+
+def test_sharded_result_is_bit_identical_to_single(faiss):
+    """Row scores do not depend on where a row lives => merge of shards == single index, bit for bit."""
+    import torch
+    from wise_b200 import _capi
+    L = _capi.lib()
+    n, d, nq, k = 80000, 768, 4, 100
+    xb = O.clustered_unit(n, d, 64, 7)
+    xq = O.clustered_unit(nq, d, 64, 8)
+    one = _flat(faiss, xb)
+    D1, I1 = one.search(xq, k)
+    st = torch.cuda.current_stream().cuda_stream
+    G = 8
+    Dp = torch.empty(G, nq, k, device="cuda"); Ip = torch.empty(G, nq, k, dtype=torch.int64, device="cuda")
+    keep = []
+    for r in range(G):
+        a, b = n * r // G, n * (r + 1) // G
+        idx = faiss.IndexIDMap(faiss.IndexFlatIP(d))
+        idx.add_with_ids(xb[a:b], np.arange(a, b, dtype=np.int64))
+        keep.append(idx)
+        qd = torch.from_numpy(xq).cuda()
+        _capi.check(L.wb_search_dev(idx._h, nq, qd.data_ptr(), k, 1, Dp[r].data_ptr(), Ip[r].data_ptr(), st))
+    Dm = torch.empty(nq, k, device="cuda"); Im = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+    _capi.check(L.wb_merge_topk_dev(0, nq, k, G, Dp.data_ptr(), Ip.data_ptr(), Dm.data_ptr(), Im.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert np.array_equal(Im.cpu().numpy(), I1) and np.array_equal(Dm.cpu().numpy(), D1)
+
+
+def test_reconstruct_and_export(faiss):
+    xb = O.unit_gaussian(5000, 70, 5)  # d % 4 != 0: padded row stride in HBM
+    ids = np.arange(5000, dtype=np.int64) * 3 + 7
+    idx = _flat(faiss, xb, ids)
+    x, i, _ = idx._export(100, 50)
+    assert np.array_equal(x, xb[100:150]) and np.array_equal(i, ids[100:150])
+    rec = faiss._reconstruct(idx, [7, 3 * 4999 + 7, 3 * 17 + 7])
+    assert np.array_equal(rec, xb[[0, 4999, 17]])
+    with pytest.raises(RuntimeError):
+        faiss._reconstruct(idx, [8])
+
+
+def test_large_scan_properties_2m_x_768(faiss):
+    """Size-independent checks at a size the oracle cannot brute-force quickly: returned scores equal
+    fp64 recomputation within 1e-5, rows sorted, and no row in a 200k-row sample beats the k-th score."""
+    import torch
+    from wise_b200 import _capi
+    L = _capi.lib()
+    n, d, k, nq = 2_000_000, 768, 100, 3
+    gen = torch.Generator(device="cuda"); gen.manual_seed(2024)
+    x = torch.randn(n, d, device="cuda", generator=gen)
+    x /= x.norm(dim=1, keepdim=True)
+    q = x[[5, 1_000_000, n - 1]].clone() * 0.7 + 0.3 * torch.nn.functional.normalize(torch.randn(nq, d, device="cuda", generator=gen), dim=1)
+    q = torch.nn.functional.normalize(q, dim=1).contiguous()
+    idx = faiss.IndexFlatIP(d)
+    idx.reserve(n)
+    _capi.check(L.wb_add_with_ids_dev(idx._h, n, x.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    D, I = idx.search(q.cpu().numpy(), k)
+    assert np.all(np.diff(D, axis=1) <= 0) and np.all(I >= 0)
+    assert I[0, 0] == 5 and I[1, 0] == 1_000_000 and I[2, 0] == n - 1
+    qh = q.cpu().numpy().astype(np.float64)
+    for j in range(nq):
+        rows = x[torch.from_numpy(I[j]).cuda()].cpu().numpy().astype(np.float64)
+        assert np.abs(rows @ qh[j] - D[j]).max() <= 1e-5
+        assert len(set(I[j].tolist())) == k
+    samp = torch.randint(0, n, (200_000,), device="cuda", generator=gen)
+    s = (x[samp].double() @ q.double().T).cpu().numpy()  # [200k, nq]
+    samp_h = samp.cpu().numpy()
+    for j in range(nq):
+        better = samp_h[s[:, j] > D[j, -1] + 2e-6]
+        assert set(better.tolist()) <= set(I[j].tolist())

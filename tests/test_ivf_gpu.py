@@ -1,0 +1,117 @@
+"""GPU parity tests for IndexIVFFlat (coarse quantizer, list scan, add, k-means) vs the CPU oracle.
+Search is compared on the oracle's own centroids so k-means randomness is out of the picture
+(BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def faiss():
+    from wise_b200 import faiss_compat
+    return faiss_compat
+
+
+def _ivf(faiss, xb, ids, cent):
+    q = faiss.IndexFlatIP(xb.shape[1])
+    idx = faiss.IndexIVFFlat(q, xb.shape[1], cent.shape[0], faiss.METRIC_INNER_PRODUCT)
+    assert not idx.is_trained
+    idx.set_centroids(cent)
+    assert idx.is_trained and q.ntotal == cent.shape[0]
+    for s in range(0, xb.shape[0], 512):
+        idx.add_with_ids(xb[s:s + 512], ids[s:s + 512])
+    return idx
+
+
+@pytest.mark.parametrize("n,d,nlist,k", [(20000, 64, 32, 10), (60000, 512, 300, 100), (30000, 768, 128, 100), (5000, 30, 7, 1000)])
+def test_ivf_search_matches_oracle(faiss, n, d, nlist, k):
+    xb = O.clustered_unit(n, d, 2 * nlist, 50)
+    xq = O.clustered_unit(6, d, 2 * nlist, 51)
+    cent = O.kmeans_init(xb, nlist)
+    ids = np.arange(n, dtype=np.int64) * 5 + 2
+    idx = _ivf(faiss, xb, ids, cent)
+    assert idx.ntotal == n and idx.nprobe == 1
+    a = O.ivf_assign(xb, cent)
+    _, _, ga = idx._export(0, n, want_assign=True)
+    assert (ga == a).mean() > 0.9999  # argmax ties / fp32 noise may move a handful of rows
+    a = ga.astype(np.int64)  # compare search on identical lists
+    for nprobe in (1, 8, 32, 4096):
+        idx.nprobe = nprobe
+        D, I = idx.search(xq, k)
+        Dr, Ir = O.ivf_search(xb, ids, a, cent, xq, k, nprobe)
+        O.compare_topk(D, I, Dr, Ir)
+    Df, If = O.flat_search(xb, xq, k, ids)  # nprobe >= nlist is exhaustive
+    O.compare_topk(D, I, Df, If)
+    D1, I1 = idx.search(xq[:1], k)
+    O.compare_topk(D1, I1, Df[:1], If[:1])
+
+
+def test_ivf_untrained_and_surface(faiss):
+    q = faiss.IndexFlatIP(16)
+    idx = faiss.IndexIVFFlat(q, 16, 4, faiss.METRIC_INNER_PRODUCT)
+    assert hasattr(idx, "nprobe") and hasattr(idx, "direct_map") and idx.direct_map.type == idx.direct_map.NoMap
+    with pytest.raises(RuntimeError):
+        idx.add_with_ids(O.unit_gaussian(3, 16, 0), np.arange(3))
+    idx.parallel_mode = 1  # api/routes.py:901
+    idx.set_centroids(O.unit_gaussian(4, 16, 1))
+    xb = O.unit_gaussian(100, 16, 2)
+    idx.add_with_ids(xb, np.arange(1, 101))  # WISE ids start at 1
+    with pytest.raises(RuntimeError):
+        idx.make_direct_map(True)  # faiss: "direct map supported only for seqential ids"
+    with pytest.raises(RuntimeError):
+        idx.reconstruct_batch([1])
+    idx2 = faiss.IndexIVFFlat(faiss.IndexFlatIP(16), 16, 4, faiss.METRIC_INNER_PRODUCT)
+    idx2.set_centroids(O.unit_gaussian(4, 16, 1))
+    idx2.add_with_ids(xb, np.arange(100))
+    idx2.make_direct_map(True)
+    assert idx2.direct_map.type != idx2.direct_map.NoMap
+    assert np.array_equal(idx2.reconstruct_batch([5, 99, 0]), xb[[5, 99, 0]])
+
+
+def test_kmeans_one_iteration_matches_oracle(faiss):
+    """From identical starting centroids, one GPU iteration == one oracle iteration."""
+    import ctypes as C
+    import torch
+    from wise_b200 import _capi
+    L = _capi.lib()
+    n, d, k = 6000, 48, 40
+    x = O.clustered_unit(n, d, 60, 9)
+    c0 = O.kmeans_init(x, k)
+    idx = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, k, faiss.METRIC_INNER_PRODUCT)
+    idx.set_centroids(c0)
+    xd = torch.from_numpy(x).cuda()
+    assign = torch.empty(n, dtype=torch.int32, device="cuda")
+    sums = torch.empty(k, d, device="cuda"); counts = torch.empty(k, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    obj = C.c_double(0)
+    _capi.check(L.wb_kmeans_assign_dev(idx._h, n, xd.data_ptr(), assign.data_ptr(), C.byref(obj), st))
+    _capi.check(L.wb_kmeans_accumulate_dev(idx._h, n, xd.data_ptr(), assign.data_ptr(), sums.data_ptr(), counts.data_ptr(), st))
+    nsplit = C.c_int64(0)
+    _capi.check(L.wb_kmeans_update_dev(idx._h, sums.data_ptr(), counts.data_ptr(), n, 1234, C.byref(nsplit), st))
+    torch.cuda.synchronize()
+    c1_ref, a_ref, obj_ref, nsplit_ref = O.kmeans_iteration(x, c0)
+    assert (assign.cpu().numpy() == a_ref).mean() > 0.9995
+    assert abs(obj.value - obj_ref) < 1e-3 * n * 1e-2
+    assert nsplit.value == nsplit_ref
+    assert np.abs(idx.centroids() - c1_ref).max() < 1e-4
+
+
+def test_train_end_to_end_objective(faiss):
+    n, d, k = 8000, 64, 50
+    x = O.clustered_unit(n, d, 50, 21)
+    idx = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, k, faiss.METRIC_INNER_PRODUCT)
+    idx.train(x)
+    assert idx.is_trained and idx.quantizer.ntotal == k
+    c = idx.centroids()
+    assert np.allclose(np.linalg.norm(c, axis=1), 1.0, atol=1e-4)
+    c_ref, objs = O.kmeans_train(x, k)
+    obj_gpu = float(np.max(x.astype(np.float64) @ c.astype(np.float64).T, axis=1).sum())
+    obj_ref = float(np.max(x.astype(np.float64) @ c_ref.astype(np.float64).T, axis=1).sum())
+    assert obj_gpu >= 0.995 * obj_ref, (obj_gpu, obj_ref)
+    idx.add(x)
+    idx.nprobe = 5
+    D, I = idx.search(x[:4], 3)
+    assert np.array_equal(I[:, 0], np.arange(4))

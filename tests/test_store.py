@@ -1,0 +1,113 @@
+"""FeatureStore layout tests, mirroring /root/reference/src/feature/store/test_feature_store.py,
+plus the fixture written by the reference's own NumpySaveStore (tests/golden/make_golden.py)."""
+import os
+import pickle
+import tarfile
+
+import numpy as np
+import pytest
+
+from wise_b200.store import FeatureStoreFactory, NumpySaveStore, WebdatasetStore, decode_features
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+A = np.array([[1, 2, 3, 4]])
+B = np.array([[5, 6, 7, 8]])
+Cc = np.array([[9, 10, 11, 12]])
+
+
+def test_reads_reference_written_numpy_store():
+    exp = np.load(os.path.join(GOLD, "numpy_store_expected.npz"))
+    s = FeatureStoreFactory.load_store("video", os.path.join(GOLD, "numpy_store"))
+    assert isinstance(s, NumpySaveStore)
+    s.enable_read()
+    assert s.feature_count == int(exp["feature_count"]) == 7 and s.feature_dim == int(exp["feature_dim"]) == 8
+    ids, feats = zip(*[(int(i), v) for i, v in s])
+    assert list(ids) == exp["ids"].tolist()
+    assert np.array_equal(np.concatenate(feats, 0), exp["features"])
+    bi, bf = zip(*s.iter_batch(4))
+    assert np.array_equal(np.concatenate(bi), exp["ids"]) and np.array_equal(np.concatenate(bf), exp["features"])
+    assert bi[0].dtype == np.int64 and bf[0].dtype == np.float32
+
+
+def test_numpy_save_store_round_trip(tmp_path):  # reference test_numpy_save_store
+    w = NumpySaveStore("test-store", tmp_path)
+    w.enable_write(3, -1, verbose=0)
+    seq = [A, B, Cc, Cc, B, A, B]
+    for i, f in enumerate(seq):
+        w.add(i, f)
+    w.close()
+    r = NumpySaveStore("test-store", tmp_path)
+    r.enable_read()
+    loaded = {int(i): v for i, v in r}
+    assert r.feature_count == 7 and r.feature_dim == 4
+    for i, f in enumerate(seq):
+        assert np.all(np.equal(loaded[i], f))
+    assert sorted(os.listdir(tmp_path)) == ["test-store-000000.npz", "test-store-000001.npz", "test-store-000002.npz"]
+
+
+def test_webdataset_store_batch_write(tmp_path):  # reference test_webdataset_store_batch_write
+    f0 = np.concatenate((A, B, Cc), axis=0)
+    f3 = np.concatenate((Cc, B, A), axis=0)
+    w = WebdatasetStore("test-store", tmp_path)
+    w.enable_write(3, 256)
+    w.add(0, f0)
+    w.add(3, f3)
+    w.close()
+    r = WebdatasetStore("test-store", tmp_path)
+    r.enable_read(shard_shuffle=False, shuffle_values=False)
+    got = {int(i): v for i, v in r}
+    assert np.all(np.equal(got[0], f0)) and np.all(np.equal(got[3], f3))
+
+
+def test_webdataset_store_read_order(tmp_path):  # reference test_webdataset_store_read_order
+    f0 = np.concatenate((A, B, Cc), axis=0)
+    f3 = np.concatenate((Cc, B, A), axis=0)
+    w = WebdatasetStore("test-store", tmp_path)
+    w.enable_write(3, 256, verbose=0)
+    for i, f in ((0, f0), (3, f3), (6, A), (7, B), (8, Cc)):
+        w.add(i, f)
+    w.close()
+    r = WebdatasetStore("test-store", tmp_path)
+    r.enable_read(shard_shuffle=False, shuffle_values=False)
+    assert [int(i) for i, _ in r] == [0, 3, 6, 7, 8]
+    assert r.feature_count == 5 and r.feature_dim == 4
+
+
+def test_webdataset_member_layout_and_batches(tmp_path):
+    """`%010d.features.pyd` members holding pickle.dumps(ndarray (1,d) f32) - webdataset_store.py:93-99."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((1100, 16)).astype(np.float32)
+    w = WebdatasetStore("video", tmp_path)
+    w.enable_write(500, 1 << 30)
+    for i in range(x.shape[0]):
+        w.add(i + 1, x[i:i + 1])
+    w.close()
+    files = sorted(os.listdir(tmp_path))
+    assert files == ["video-000000.tar", "video-000001.tar", "video-000002.tar"]
+    with tarfile.open(tmp_path / files[0]) as tf:
+        m = tf.getmembers()[0]
+        assert m.name == "0000000001.features.pyd"
+        v = pickle.loads(tf.extractfile(m).read())
+        assert v.shape == (1, 16) and v.dtype == np.float32
+    s = FeatureStoreFactory.load_store("video", tmp_path)
+    assert isinstance(s, WebdatasetStore)
+    s.enable_read()
+    assert (s.feature_count, s.feature_dim) == (1100, 16)
+    sizes, ids_all, xs = [], [], []
+    for ids, feats in s.iter_batch():
+        sizes.append(len(ids)); ids_all.append(ids); xs.append(feats)
+    assert sizes == [512, 512, 76]
+    assert np.array_equal(np.concatenate(ids_all), np.arange(1, 1101)) and np.array_equal(np.concatenate(xs), x)
+
+
+def test_unpickler_rejects_non_numpy():
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("true",))
+    with pytest.raises(pickle.UnpicklingError):
+        decode_features(pickle.dumps(Evil()))
+
+
+def test_factory_rejects_mixed_or_missing(tmp_path):
+    with pytest.raises(ValueError):
+        FeatureStoreFactory.load_store("video", tmp_path)

@@ -155,7 +155,11 @@ def _gather_rows(index, rows: np.ndarray) -> np.ndarray:
 
 # ------------------------------------------------------------------------------------------------
 def read_index(fname: str, io_flags: int = 0):
-    with open(fname, "rb") as f:
+    try:
+        f = open(fname, "rb")
+    except OSError as e:  # faiss raises RuntimeError from its FileIOReader
+        raise RuntimeError(f"could not open {fname} for reading: {e.strerror}") from e
+    with f:
         return _read_any(f)
 
 

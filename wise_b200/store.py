@@ -1,0 +1,319 @@
+"""FeatureStore readers/writers that keep WISE's on-disk layout, without the `webdataset` package.
+
+Mirrors /root/reference/src/feature/store/{feature_store.py, webdataset_store.py,
+numpy_save_store.py, feature_store_factory.py}: same class names, methods, file names and sample
+encoding, so stores written by either implementation are read by the other.
+
+  WebdatasetStore : shards `<name>-%06d.tar`; one tar member per sample,
+                    `%010d.features.pyd` = pickle.dumps(np.ndarray (m, d))   (webdataset_store.py:33-35,93-99)
+  NumpySaveStore  : shards `<name>-%06d.npz` with `feature_id`, `features`    (numpy_save_store.py:80-87)
+
+Differences, all on the safe side: `feature_count` is exact (the reference estimates it from
+tar sizes, webdataset_store.py:83-91); NumpySaveStore gains `iter_batch` (create_index needs it,
+feature_search_index.py:80); unpickling is restricted to numpy arrays.
+"""
+from __future__ import annotations
+
+import enum
+import glob
+import io
+import os
+import pickle
+import random
+import tarfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+
+class FeatureStore:
+    def __init__(self, store_name, store_data_dir):
+        raise NotImplementedError
+
+    def add(self, index, features):
+        raise NotImplementedError
+
+    def load(self, start_index=0, count=-1):
+        raise NotImplementedError
+
+
+class _NumpyOnlyUnpickler(pickle.Unpickler):
+    """np.load(..., allow_pickle=True) equivalent that refuses anything but ndarray pickles."""
+
+    _ALLOWED = {
+        ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+        ("numpy", "ndarray"), ("numpy", "dtype"),
+        ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+        ("numpy.core.numeric", "_frombuffer"), ("numpy._core.numeric", "_frombuffer"),
+    }
+
+    def find_class(self, module, name):
+        if (module, name) in self._ALLOWED:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"feature store sample references {module}.{name}; only numpy arrays are allowed")
+
+
+def decode_features(payload: bytes) -> np.ndarray:
+    """webdataset_store.py:113,129: np.load(BytesIO(payload), allow_pickle=True) of a `.pyd` member."""
+    if payload[:6] == b"\x93NUMPY":
+        return np.load(io.BytesIO(payload), allow_pickle=False)
+    return _NumpyOnlyUnpickler(io.BytesIO(payload)).load()
+
+
+class WebdatasetStore(FeatureStore):
+    EXTENSION = "tar"
+
+    def __init__(self, store_name, store_data_dir):
+        self.store_name = store_name
+        self.store_data_dir = str(store_data_dir)
+        self.store_data_filename = os.path.join(self.store_data_dir, self.store_name + "-%06d." + self.EXTENSION)
+        self.feature_count = -1
+        self.feature_dim = -1
+        self._tar = None
+
+    # ---- writing: webdataset.ShardWriter semantics ------------------------------------------------
+    def enable_write(self, shard_maxcount, shard_maxsize, verbose=0):
+        self.shard_maxcount = shard_maxcount
+        self.shard_maxsize = shard_maxsize if shard_maxsize and shard_maxsize > 0 else float("inf")
+        self.verbose = verbose
+        self._shard = 0
+        self._count = 0
+        self._size = 0
+        self._tar = None
+
+    def _next_stream(self):
+        if self._tar is not None:
+            self._tar.close()
+        fname = self.store_data_filename % self._shard
+        if self.verbose:
+            print("# writing", fname, self._count)
+        self._shard += 1
+        self._tar = tarfile.open(fname, "w")  # plain tar, like ShardWriter
+        self._count = 0
+        self._size = 0
+
+    def add(self, id, features):
+        if getattr(self, "shard_maxcount", None) is None:
+            raise ValueError("enable_write() must be activated before invoking add() method")
+        if self._tar is None or self._count >= self.shard_maxcount or self._size >= self.shard_maxsize:
+            self._next_stream()
+        data = pickle.dumps(features)  # webdataset's default encoder for the "pyd" extension
+        ti = tarfile.TarInfo("%010d" % id + ".features.pyd")
+        ti.size = len(data)
+        ti.mtime = time.time()
+        ti.mode = 0o444
+        ti.uname = "bigdata"
+        ti.gname = "bigdata"
+        self._tar.addfile(ti, io.BytesIO(data))
+        self._count += 1
+        self._size += len(data) + 512 + (-len(data)) % 512
+
+    def close(self):
+        if self._tar is not None:
+            self._tar.close()
+            self._tar = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reading ----------------------------------------------------------------------------------
+    def shard_files(self):
+        """Shards {first..last} in ascending index order (webdataset brace expansion, :53-67)."""
+        prefix = os.path.join(self.store_data_dir, self.store_name + "-")
+        found = {}
+        for fn in glob.iglob(prefix + "*.tar"):
+            tok = fn[len(prefix):].split(".tar")[0]
+            found[int(tok)] = (tok, fn)
+        if not found:
+            return []
+        lo, hi = min(found), max(found)
+        width = len(found[lo][0])
+        return [prefix + str(i).zfill(width) + ".tar" for i in range(lo, hi + 1)]
+
+    def enable_read(self, shard_shuffle=False, shuffle_values=False, shuffle_bufsize=10000):
+        self.shard_shuffle = shard_shuffle
+        self.shuffle_values = shuffle_values
+        self.shuffle_bufsize = shuffle_bufsize
+        files = self.shard_files()
+        self.feature_count = 0
+        self.feature_dim = -1
+        for fn in files:
+            with tarfile.open(fn) as tf:
+                for m in tf:
+                    if not m.isreg():
+                        continue
+                    if self.feature_dim < 0:
+                        self.feature_dim = decode_features(tf.extractfile(m).read()).shape[1]
+                    self.feature_count += 1
+
+    def _samples(self):
+        files = self.shard_files()
+        if self.shard_shuffle:
+            files = list(files)
+            random.shuffle(files)  # webdataset shuffles shard order with a time-seeded RNG
+        for fn in files:
+            with tarfile.open(fn) as tf:
+                for m in tf:
+                    if not m.isreg():
+                        continue
+                    key, _, ext = os.path.basename(m.name).partition(".")
+                    if ext != "features.pyd":
+                        continue
+                    yield int(key), decode_features(tf.extractfile(m).read())
+
+    def _maybe_shuffled(self):
+        it = self._samples()
+        if not self.shuffle_values:
+            yield from it
+            return
+        buf = []
+        for s in it:  # webdataset .shuffle(bufsize): reservoir-style buffer shuffle
+            buf.append(s)
+            if len(buf) >= self.shuffle_bufsize:
+                yield buf.pop(random.randrange(len(buf)))
+        random.shuffle(buf)
+        yield from buf
+
+    def __iter__(self):
+        yield from self._maybe_shuffled()
+
+    def iter_batch(self, batch_size=512):
+        """(ids int64[b], features float32[b, d]) batches; (1, d) samples squeezed like :131-139."""
+        ids, vecs = [], []
+        for fid, vec in self._maybe_shuffled():
+            ids.append(fid)
+            vecs.append(np.squeeze(vec, axis=0))
+            if len(ids) == batch_size:
+                yield np.asarray(ids, np.int64), np.stack(vecs)
+                ids, vecs = [], []
+        if ids:
+            yield np.asarray(ids, np.int64), np.stack(vecs)
+
+
+class NumpySaveStore(FeatureStore):
+    def __init__(self, store_name, store_data_dir):
+        self.store_name = store_name
+        self.store_data_dir = Path(store_data_dir)
+
+    def enable_write(self, shard_maxcount, shard_maxsize, verbose=0):
+        self.shard_maxcount = shard_maxcount
+        self.shard_maxsize = shard_maxsize
+        self.verbose = verbose
+        self.current_shard_index = -1
+
+    def enable_read(self, shard_shuffle=False, shuffle_values=False, shuffle_bufsize=10000):
+        self.shard_shuffle = shard_shuffle
+        self.shuffle_values = shuffle_values
+        self.shuffle_bufsize = shuffle_bufsize
+        pattern = self.store_data_dir / (self.store_name + "-*.npz")
+        self.npz_filename_list = list(glob.iglob(pattern.as_posix()))
+        if self.shard_shuffle:
+            random.shuffle(self.npz_filename_list)
+        else:
+            self.npz_filename_list.sort()
+        self.feature_count = 0
+        self.feature_dim = -1
+        for fn in self.npz_filename_list:
+            with np.load(fn) as payload:
+                self.feature_count += payload["feature_id"].shape[0]
+                if self.feature_dim < 0:
+                    f0 = payload["features"][0]
+                    if f0.ndim not in (1, 2):
+                        raise ValueError(f"unrecognized feature shape {f0.shape}")
+                    self.feature_dim = f0.shape[-1]
+
+    def add(self, id, features):
+        if self.current_shard_index == -1:
+            self.feature_dim = features.shape[1]
+            self.shard_features = np.ndarray((self.shard_maxcount, self.feature_dim), dtype=np.float32)
+            self.shard_feature_id = np.ndarray((self.shard_maxcount), dtype=np.int32)
+            self.shard_feature_index = 0
+            self.current_shard_index = 0
+        if self.feature_dim != features.shape[1]:
+            raise ValueError(f"feature dimension cannot change and must be {self.feature_dim}")
+        if features.shape[0] != 1:
+            raise ValueError(f"cannot add {features.shape[0]} features, only one feature can be added at a time")
+        if self.shard_feature_index == self.shard_maxcount:
+            self.save_current_shard()
+            self.add(id, features)
+        else:
+            self.shard_features[self.shard_feature_index] = features
+            self.shard_feature_id[self.shard_feature_index] = id
+            self.shard_feature_index += 1
+
+    def save_current_shard(self):
+        shard_id = "%s-%06d" % (self.store_name, self.current_shard_index)
+        np.savez(self.store_data_dir / shard_id, feature_id=self.shard_feature_id, features=self.shard_features)
+        if self.verbose:
+            print(f"saved {self.shard_feature_index} features to shard {shard_id}")
+        self.current_shard_index += 1
+        self.shard_feature_index = 0
+
+    def _shards(self):
+        for fn in self.npz_filename_list:
+            with np.load(fn) as payload:
+                yield payload["feature_id"], payload["features"]
+
+    def __iter__(self):
+        for ids, feats in self._shards():
+            n = ids.shape[0]
+            order = random.sample(range(n), n) if self.shuffle_values else range(n)
+            for i in order:
+                yield ids[i], np.take(feats, [i], 0)  # (1, d), like the reference
+
+    def iter_batch(self, batch_size=512):
+        """Not in the reference (its create_index could only consume WebdatasetStore); same contract."""
+        for ids, feats in self._shards():
+            feats = feats.reshape(ids.shape[0], -1)
+            for s in range(0, ids.shape[0], batch_size):
+                yield ids[s:s + batch_size].astype(np.int64), np.ascontiguousarray(feats[s:s + batch_size], np.float32)
+
+    def close(self):
+        if getattr(self, "shard_feature_index", 0) != 0:
+            self.shard_feature_id = self.shard_feature_id[: self.shard_feature_index].copy()
+            self.shard_features = self.shard_features[: self.shard_feature_index].copy()
+            self.save_current_shard()
+            self.shard_feature_index = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "shard_feature_index", 0) != 0:
+                self.close()
+        except Exception:
+            pass
+
+
+class FeatureStoreType(str, enum.Enum):
+    WEBDATASET = "webdataset"
+    NUMPY = "numpy"
+
+
+class FeatureStoreFactory:
+    @classmethod
+    def create_store(cls, feature_store_type, media_type, features_dir):
+        if feature_store_type == FeatureStoreType.WEBDATASET:
+            return WebdatasetStore(media_type, features_dir)
+        if feature_store_type == FeatureStoreType.NUMPY:
+            return NumpySaveStore(media_type, features_dir)
+        raise ValueError(f"unknown feature_store_type {feature_store_type}")
+
+    @classmethod
+    def load_store(cls, media_type, features_dir):
+        """Infer the store type from the shard extension (feature_store_factory.py:23-38)."""
+        features_dir = Path(features_dir)
+        exts = []
+        for fn in glob.iglob((features_dir / (media_type + "-*.*")).as_posix()):
+            suffix = Path(fn).suffix
+            if suffix not in exts:
+                exts.append(suffix)
+        if len(exts) != 1:
+            raise ValueError(f"failed to infer type of {media_type} feature store in {features_dir}")
+        if exts[0] == ".tar":
+            return WebdatasetStore(media_type, features_dir)
+        if exts[0] == ".npz":
+            return NumpySaveStore(media_type, features_dir)
+        raise ValueError(f"unknown store containing shard filenames with extension {exts[0]}")
