@@ -113,6 +113,8 @@ int64_t wb_launch_count(const wb_index* h);
  * wb_search / wb_search_dev call that finished; -1 if timing was off. */
 int wb_set_timing(wb_index* h, int on);
 float wb_last_scan_ms(wb_index* h);
+/* Durations (ms) of the most recent timed scan launches, oldest first; returns how many (<= cap, <= 128). */
+int wb_scan_ms_history(wb_index* h, float* out_ms, int cap);
 
 #ifdef __cplusplus
 }

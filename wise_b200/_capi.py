@@ -50,6 +50,7 @@ SIGNATURES = {
     "wb_launch_count": (C.c_int64, [_vp]),
     "wb_set_timing": (C.c_int, [_vp, C.c_int]),
     "wb_last_scan_ms": (C.c_float, [_vp]),
+    "wb_scan_ms_history": (C.c_int, [_vp, _f32p, C.c_int]),
 }
 
 _lib = None

@@ -99,8 +99,9 @@ struct wb_index {
     // accounting
     int64_t launches = 0;
     bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    static constexpr int kEvRing = 128;  // event pairs of the most recent timed scan launches
+    cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
+    int64_t ev_count = 0;
 };
 
 static int set_dev(const wb_index* h) {
@@ -132,8 +133,10 @@ static int create_common(int d, int device, bool ivf, int64_t nlist, wb_index** 
     h->sm_count = prop.multiProcessorCount;
     h->smem_max = (int)prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&h->ev0));
-    CK(cudaEventCreate(&h->ev1));
+    for (int i = 0; i < wb_index::kEvRing; ++i) {
+        CK(cudaEventCreate(&h->ev0[i]));
+        CK(cudaEventCreate(&h->ev1[i]));
+    }
     if (ivf) {
         CK(cudaMalloc(&h->centroids, (size_t)nlist * h->ld * sizeof(float)));
         CK(cudaMemsetAsync(h->centroids, 0, (size_t)nlist * h->ld * sizeof(float), h->stream));
@@ -163,8 +166,10 @@ extern "C" int wb_free(wb_index* h) {
     for (DevBuf* b : {&h->parts, &h->qbuf, &h->dbuf, &h->ibuf, &h->pD, &h->pI, &h->xbuf, &h->idbuf, &h->misc,
                       &h->kperm, &h->koff})
         b->release();
-    cudaEventDestroy(h->ev0);
-    cudaEventDestroy(h->ev1);
+    for (int i = 0; i < wb_index::kEvRing; ++i) {
+        cudaEventDestroy(h->ev0[i]);
+        cudaEventDestroy(h->ev1[i]);
+    }
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -179,16 +184,27 @@ extern "C" int64_t wb_launch_count(const wb_index* h) { return h ? h->launches :
 extern "C" int wb_set_timing(wb_index* h, int on) {
     if (!h) return fail("NULL index");
     h->timing = on != 0;
-    h->ev_valid = false;
+    h->ev_count = 0;
     return 0;
 }
-extern "C" float wb_last_scan_ms(wb_index* h) {
-    if (!h || !h->ev_valid) return -1.f;
-    if (cudaSetDevice(h->device) != cudaSuccess) return -1.f;
-    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.f;
+static float scan_ms_at(wb_index* h, int64_t i) {
+    const int s = (int)(i % wb_index::kEvRing);
+    if (cudaEventSynchronize(h->ev1[s]) != cudaSuccess) return -1.f;
     float ms = -1.f;
-    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev0[s], h->ev1[s]) != cudaSuccess) return -1.f;
     return ms;
+}
+extern "C" float wb_last_scan_ms(wb_index* h) {
+    if (!h || h->ev_count == 0) return -1.f;
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1.f;
+    return scan_ms_at(h, h->ev_count - 1);
+}
+extern "C" int wb_scan_ms_history(wb_index* h, float* out_ms, int cap) {
+    if (!h || !out_ms || cap <= 0) return 0;
+    if (cudaSetDevice(h->device) != cudaSuccess) return 0;
+    const int64_t n = std::min<int64_t>(std::min<int64_t>(h->ev_count, wb_index::kEvRing), cap);
+    for (int64_t i = 0; i < n; ++i) out_ms[i] = scan_ms_at(h, h->ev_count - n + i);
+    return (int)n;
 }
 extern "C" int wb_storage(wb_index* h, void** rows_dev, int64_t* ld) {
     if (!h) return fail("NULL index");
@@ -365,7 +381,8 @@ static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const fl
     p.ld = h->ld;
     p.k = k;
     p.nparts = (int)S;
-    if (timed && h->timing) CK(cudaEventRecord(h->ev0, st));
+    const int evs = (int)(h->ev_count % wb_index::kEvRing);
+    if (timed && h->timing) CK(cudaEventRecord(h->ev0[evs], st));
     const int64_t max_y = 32768;
     for (int64_t g0 = 0; g0 < qgroups_total; g0 += max_y) {
         const int64_t gy = std::min(max_y, qgroups_total - g0);
@@ -377,8 +394,8 @@ static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const fl
         h->launches++;
     }
     if (timed && h->timing) {
-        CK(cudaEventRecord(h->ev1, st));
-        h->ev_valid = true;
+        CK(cudaEventRecord(h->ev1[evs], st));
+        h->ev_count++;
     }
     return launch_merge_keys(h, nq, k, S, h->parts.as<uint64_t>(), ids, D, I, st);
 }
@@ -521,7 +538,8 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
     p.perm = h->perm;
     p.list_off = h->list_off;
     p.nprobe = np;
-    if (h->timing) CK(cudaEventRecord(h->ev0, st));
+    const int evs = (int)(h->ev_count % wb_index::kEvRing);
+    if (h->timing) CK(cudaEventRecord(h->ev0[evs], st));
     const int64_t max_y = 32768;
     for (int64_t q0 = 0; q0 < nq; q0 += max_y) {
         const int64_t gy = std::min(max_y, nq - q0);
@@ -533,8 +551,8 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
         h->launches++;
     }
     if (h->timing) {
-        CK(cudaEventRecord(h->ev1, st));
-        h->ev_valid = true;
+        CK(cudaEventRecord(h->ev1[evs], st));
+        h->ev_count++;
     }
     return launch_merge_keys(h, nq, (int)k, S, h->parts.as<uint64_t>(), h->ids, D, I, st);
 }
