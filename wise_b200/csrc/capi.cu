@@ -343,18 +343,38 @@ static int launch_scan(const ScanCfg& c, bool gather, ScanParams& p, dim3 grid, 
     return fail("bad NQ %d", c.NQ);
 }
 
+// Sort-buffer size of the merge: everything at once when it is small, else k + a 2048-entry queue.
+static int merge_buffer_entries(int k, int64_t nparts) {
+    const int64_t M = nparts * (int64_t)k;
+    const int full = pow2_ceil(k + 2 * kMergeThreads);
+    if (M <= full) return std::max(2, pow2_ceil((int)std::max<int64_t>(M, k)));
+    return full;
+}
+
+template <bool FROM_KEYS>
+static int merge_smem_optin() {
+    static thread_local bool done[64] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev >= 64 || !done[dev]) {
+        CK(cudaFuncSetAttribute(merge_topk_kernel<FROM_KEYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        if (dev < 64) done[dev] = true;
+    }
+    return 0;
+}
+
 static int launch_merge_keys(wb_index* h, int64_t nq, int k, int64_t nparts, const uint64_t* keys, const int64_t* ids,
                              float* D, int64_t* I, cudaStream_t st) {
     MergeParams m{};
     m.nq = nq;
     m.k = k;
     m.nparts = nparts;
-    const int64_t M = nparts * k;
-    m.S = std::max(pow2_ceil(2 * k), (int)std::min<int64_t>(pow2_ceil((int)std::min<int64_t>(M, 4096)), 4096));
+    m.S = merge_buffer_entries(k, nparts);
     m.keys = keys;
     m.ids = ids;
     m.D = D;
     m.I = I;
+    TRY(merge_smem_optin<true>());
     merge_topk_kernel<true><<<(unsigned)nq, kMergeThreads, (size_t)m.S * 8, st>>>(m);
     CK(cudaGetLastError());
     h->launches++;
@@ -628,12 +648,12 @@ extern "C" int wb_merge_topk_dev(int device, int64_t nq, int64_t k, int64_t npar
     m.nq = nq;
     m.k = (int)k;
     m.nparts = nparts;
-    const int64_t M = nparts * k;
-    m.S = std::max(pow2_ceil(2 * (int)k), (int)std::min<int64_t>(pow2_ceil((int)std::min<int64_t>(M, 4096)), 4096));
+    m.S = merge_buffer_entries((int)k, nparts);
     m.Dp = D_parts_dev;
     m.Ip = I_parts_dev;
     m.D = D_dev;
     m.I = I_dev;
+    TRY(merge_smem_optin<false>());
     merge_topk_kernel<false><<<(unsigned)nq, kMergeThreads, (size_t)m.S * 8, (cudaStream_t)stream>>>(m);
     CK(cudaGetLastError());
     return 0;

@@ -15,7 +15,7 @@ struct MergeParams {
     int64_t nq;
     int k;
     int64_t nparts;
-    int S;  // sort buffer entries (power of two, >= 2k)
+    int S;  // sort buffer entries: power of two >= k + 2 * kMergeThreads (or >= all candidates)
     // source A: keys [nq][nparts][k] from scan_topk_kernel; positions -> ids via ids/id_base
     const uint64_t* keys;
     const int64_t* ids;  // may be null: id = position
@@ -26,39 +26,61 @@ struct MergeParams {
     int64_t* I;  // [nq][k]
 };
 
+// Candidate c of query q as a sortable key (0 = empty slot).
+template <bool FROM_KEYS>
+__device__ __forceinline__ uint64_t merge_load(const MergeParams& p, int64_t q, int64_t M, int64_t c) {
+    if constexpr (FROM_KEYS) {
+        return p.keys[q * M + c];
+    } else {
+        const int64_t part = c / p.k, slot = c - part * p.k;
+        const int64_t src = (part * p.nq + q) * p.k + slot;
+        return p.Ip[src] >= 0 ? make_key(p.Dp[src], (uint32_t)c) : 0ull;
+    }
+}
+
+// buf = [ best k (sorted) | queue ].  Round 0 sorts the first S candidates; after that a candidate
+// is queued only if it beats the current k-th best, so almost everything dies on one compare and
+// the buffer is re-sorted only when the queue could overflow.
 template <bool FROM_KEYS>
 __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergeParams p) {
     extern __shared__ __align__(16) unsigned char smem_merge[];
-    unsigned char* smem = smem_merge;
-    uint64_t* buf = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* buf = reinterpret_cast<uint64_t*>(smem_merge);
+    __shared__ int cnt;
     const int tid = threadIdx.x;
     const int64_t q = blockIdx.x;
     const int k = p.k, S = p.S;
     const int64_t M = p.nparts * (int64_t)k;
-    int keep = 0;
-    for (int64_t next = 0; next < M || keep == 0;) {
-        const int room = S - keep;
-        const int take = (int)min((int64_t)room, M - next);
-        for (int i = tid; i < room; i += kMergeThreads) {
-            uint64_t key = 0ull;
-            if (i < take) {
-                const int64_t c = next + i;
-                if constexpr (FROM_KEYS) {
-                    key = p.keys[q * M + c];
-                } else {
-                    const int64_t part = c / k, slot = c - part * k;
-                    const int64_t src = (part * p.nq + q) * k + slot;
-                    if (p.Ip[src] >= 0) key = make_key(p.Dp[src], (uint32_t)c);
-                }
-            }
-            buf[keep + i] = key;
+    const int first = (int)min((int64_t)S, M);
+    for (int i = tid; i < S; i += kMergeThreads) buf[i] = i < first ? merge_load<FROM_KEYS>(p, q, M, i) : 0ull;
+    if (tid == 0) cnt = 0;
+    __syncthreads();
+    bitonic_sort_desc<kMergeThreads>(buf, S, 1, tid, -1);
+    const int qcap = S - k;
+    for (int64_t base = first; base < M; base += kMergeThreads) {
+        if (base == first)
+            for (int i = k + tid; i < S; i += kMergeThreads) buf[i] = 0ull;
+        __syncthreads();
+        const uint64_t thr = buf[k - 1];
+        const int64_t c = base + tid;
+        const uint64_t key = c < M ? merge_load<FROM_KEYS>(p, q, M, c) : 0ull;
+        const bool pass = key > thr;  // also rejects empty slots (0)
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            int slot0 = 0;
+            if ((tid & 31) == 0) slot0 = atomicAdd(&cnt, __popc(m));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+            if (pass) buf[k + slot0 + __popc(m & ((1u << (tid & 31)) - 1))] = key;
         }
         __syncthreads();
-        bitonic_sort_desc<kMergeThreads>(buf, S, 1, tid, -1);
-        next += take;
-        keep = k;
-        if (take == 0) break;
+        if (cnt > qcap - kMergeThreads) {  // uniform: cnt is read after the barrier
+            bitonic_sort_desc<kMergeThreads>(buf, S, 1, tid, -1);
+            for (int i = k + tid; i < S; i += kMergeThreads) buf[i] = 0ull;
+            if (tid == 0) cnt = 0;
+            __syncthreads();
+        }
     }
+    __syncthreads();
+    if (cnt > 0) bitonic_sort_desc<kMergeThreads>(buf, S, 1, tid, -1);
     for (int j = tid; j < k; j += kMergeThreads) {
         const uint64_t key = buf[j];
         float d = -FLT_MAX;
