@@ -338,10 +338,16 @@ def run_ours(a):
 
 def main():
     a = parse()
+    # Keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner) get stderr.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":
