@@ -333,6 +333,7 @@ static int launch_scan(const ScanCfg& c, bool gather, ScanParams& p, dim3 grid, 
     p.stages = c.stages;
     p.single_copy = c.single_copy;
     p.rw = c.RW;
+    p.prefetch_idx = env_int("WB_GATHER_PREFETCH", 1);
     if (gather) return launch_scan_rw<1, true>(c.RW, p, grid, c.smem, st);
     switch (c.NQ) {
         case 1: return launch_scan_rw<1, false>(c.RW, p, grid, c.smem, st);

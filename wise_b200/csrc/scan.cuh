@@ -45,6 +45,7 @@ struct ScanParams {
     int stages;
     int single_copy;        // flat && nchunks == 1: one bulk copy per group
     int rw;                 // rows per consumer warp (4, 2 or 1); a row group is 8 * rw rows
+    int prefetch_idx;       // gather: look up the next group's row indices one iteration ahead
     uint64_t* parts;        // [nq][nparts][k] keys
     int nparts;             // == gridDim.x
     // gather mode (IVF): candidates = concatenation of the probed lists of query blockIdx.y
@@ -68,7 +69,8 @@ __host__ __device__ inline ScanSmem scan_smem_layout(int NQ, int ld, int P, int 
     L.lists = o;   o += (size_t)NQ * P * 8;
     L.bars = o;    o += (size_t)stages * 2 * 8;
     L.misc = o;    o += (size_t)NQ * 8;  // qcnt[NQ] (int) + thr_s[NQ] (float)
-    L.prefix = o;  o += nprobe > 0 ? (size_t)(nprobe + 1) * 4 + (size_t)nprobe * 4 : 0;
+    o = (o + 7) & ~(size_t)7;
+    L.prefix = o;  o += nprobe > 0 ? (size_t)nprobe * 8 + (size_t)(nprobe + 1) * 4 : 0;  // pbase[np] i64 + prefix[np+1] u32
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
@@ -102,9 +104,8 @@ struct Log2<1> { static constexpr int value = 0; };
 
 struct GatherCtx {
     const uint32_t* prefix;  // smem [nprobe + 1] exclusive prefix of probed list sizes
-    const int* plist;        // smem [nprobe]
+    const int64_t* pbase;    // smem [nprobe] CSR offset of each probed list
     const uint32_t* perm;
-    const int64_t* list_off;
     int nprobe;
 };
 
@@ -115,8 +116,7 @@ __device__ __forceinline__ uint32_t gather_row(const GatherCtx& G, uint32_t cpos
         if (G.prefix[mid] <= cpos) lo = mid;
         else hi = mid - 1;
     }
-    const int64_t slot = G.list_off[G.plist[lo]] + (int64_t)(cpos - G.prefix[lo]);
-    return G.perm[slot];
+    return G.perm[G.pbase[lo] + (int64_t)(cpos - G.prefix[lo])];
 }
 
 template <int NQ, int RW, bool GATHER>
@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     uint64_t* empty = full + p.stages;
     int* qcnt = reinterpret_cast<int*>(smem + L.misc);
     float* thr_s = reinterpret_cast<float*>(smem + L.misc) + NQ;
-    uint32_t* prefix = reinterpret_cast<uint32_t*>(smem + L.prefix);
-    int* plist = reinterpret_cast<int*>(prefix + (GATHER ? p.nprobe + 1 : 0));
+    int64_t* pbase = reinterpret_cast<int64_t*>(smem + L.prefix);
+    uint32_t* prefix = reinterpret_cast<uint32_t*>(pbase + (GATHER ? p.nprobe : 0));
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -165,21 +165,21 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         thr_s[tid] = tid < nqv ? -INFINITY : INFINITY;
     }
     int64_t total = p.nrows;
-    GatherCtx G{prefix, plist, p.perm, p.list_off, p.nprobe};
+    GatherCtx G{prefix, pbase, p.perm, p.nprobe};
     if constexpr (GATHER) {
         if (warp == 0) {  // exclusive prefix sum of the probed list sizes
             uint32_t carry = 0;
             for (int base = 0; base < p.nprobe; base += 32) {
                 const int j = base + lane;
                 uint32_t sz = 0;
-                int l = 0;
                 if (j < p.nprobe) {
                     const int64_t lid = p.probes[(size_t)blockIdx.y * p.nprobe + j];
+                    int64_t b = 0;
                     if (lid >= 0) {
-                        l = (int)lid;
-                        sz = (uint32_t)(p.list_off[lid + 1] - p.list_off[lid]);
+                        b = p.list_off[lid];
+                        sz = (uint32_t)(p.list_off[lid + 1] - b);
                     }
-                    plist[j] = l;
+                    pbase[j] = b;
                 }
                 uint32_t inc = sz;
 #pragma unroll
@@ -202,14 +202,25 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         // ================================ producer ==========================================
         int s = 0;
         uint32_t ph = 0;
+        // Row index of this lane in group g.  Only the INDEX is produced here; the pointer arithmetic
+        // that consumes the (global-memory) perm value happens one iteration later, so the load of
+        // the next group's indices is in flight while this group's copies are issued.
+        auto lookup = [&](int64_t g) -> int64_t {
+            const int64_t pos = g * kGroupRows + lane;
+            if (lane >= kGroupRows || pos >= total) return 0;
+            return GATHER ? (int64_t)gather_row(G, (uint32_t)pos) : pos;
+        };
+        int64_t row_next = blockIdx.x < ngroups ? lookup(blockIdx.x) : 0;
         for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
             const int64_t p0 = g * kGroupRows;
             const int nvalid = (int)min((int64_t)kGroupRows, total - p0);
-            const float* src = nullptr;
-            if (lane < nvalid) {
-                const int64_t row = GATHER ? (int64_t)gather_row(G, (uint32_t)(p0 + lane)) : p0 + lane;
-                src = p.rows + (size_t)row * ld;
+            int64_t row = row_next;
+            if (p.prefetch_idx) {
+                if (g + gridDim.x < ngroups) row_next = lookup(g + gridDim.x);
+            } else if (g != (int64_t)blockIdx.x) {
+                row = lookup(g);
             }
+            const float* src = p.rows + (size_t)row * ld;
             for (int ch = 0; ch < p.nchunks; ++ch) {
                 if (lane == 0) mbar_wait(&empty[s], ph ^ 1u);
                 __syncwarp();
