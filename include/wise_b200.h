@@ -109,6 +109,9 @@ int wb_ivf_add_preassigned(wb_index* h, int64_t n, const float* x_host, const in
 int wb_storage(wb_index* h, void** rows_dev, int64_t* ld);
 /* Number of this library's kernels launched on behalf of `h` since creation. */
 int64_t wb_launch_count(const wb_index* h);
+/* Tensor-core path (batches >= 9 queries): epochs of gemm_topk_kernel launched so far, and how many
+ * batches had to be repaired by the CUDA-core scan after a candidate-list overflow. */
+int wb_gemm_stats(const wb_index* h, int64_t* epochs, int64_t* fallbacks);
 /* Device time (ms, CUDA events on the index's stream) of the scan kernel(s) of the last
  * wb_search / wb_search_dev call that finished; -1 if timing was off. */
 int wb_set_timing(wb_index* h, int on);

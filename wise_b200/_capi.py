@@ -48,6 +48,7 @@ SIGNATURES = {
     "wb_ivf_add_preassigned": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),
     "wb_storage": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "wb_launch_count": (C.c_int64, [_vp]),
+    "wb_gemm_stats": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "wb_set_timing": (C.c_int, [_vp, C.c_int]),
     "wb_last_scan_ms": (C.c_float, [_vp]),
     "wb_scan_ms_history": (C.c_int, [_vp, _f32p, C.c_int]),

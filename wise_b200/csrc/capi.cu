@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/wise_b200.h"
+#include "gemm.cuh"
 #include "kmeans.cuh"
 #include "merge.cuh"
 #include "scan.cuh"
@@ -92,7 +93,8 @@ struct wb_index {
     int64_t* list_off = nullptr;  // [nlist + 1]
     bool csr_dirty = true;
     // scratch
-    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff;
+    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gkeys, gstate;
+    int64_t gemm_launches = 0, gemm_fallbacks = 0;
     // device properties
     int sm_count = 148;
     int smem_max = 0;
@@ -164,7 +166,7 @@ extern "C" int wb_free(wb_index* h) {
     cudaFree(h->perm);
     cudaFree(h->list_off);
     for (DevBuf* b : {&h->parts, &h->qbuf, &h->dbuf, &h->ibuf, &h->pD, &h->pI, &h->xbuf, &h->idbuf, &h->misc,
-                      &h->kperm, &h->koff})
+                      &h->kperm, &h->koff, &h->gimg, &h->gkeys, &h->gstate})
         b->release();
     for (int i = 0; i < wb_index::kEvRing; ++i) {
         cudaEventDestroy(h->ev0[i]);
@@ -181,6 +183,12 @@ extern "C" int wb_is_trained(const wb_index* h) { return h && h->trained; }
 extern "C" int64_t wb_nlist(const wb_index* h) { return h ? h->nlist : -1; }
 extern "C" int wb_is_ivf(const wb_index* h) { return h && h->ivf; }
 extern "C" int64_t wb_launch_count(const wb_index* h) { return h ? h->launches : -1; }
+extern "C" int wb_gemm_stats(const wb_index* h, int64_t* epochs, int64_t* fallbacks) {
+    if (!h) return fail("NULL index");
+    if (epochs) *epochs = h->gemm_launches;
+    if (fallbacks) *fallbacks = h->gemm_fallbacks;
+    return 0;
+}
 extern "C" int wb_set_timing(wb_index* h, int on) {
     if (!h) return fail("NULL index");
     h->timing = on != 0;
@@ -421,6 +429,169 @@ static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const fl
     return launch_merge_keys(h, nq, k, S, h->parts.as<uint64_t>(), ids, D, I, st);
 }
 
+// ---- K2: tensor-core batched scan ---------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_tensormap_encoder(PFN_encodeTiled* out) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !p) return fail("cuTensorMapEncodeTiled is not available in this driver");
+        fn = (PFN_encodeTiled)p;
+    }
+    *out = fn;
+    return 0;
+}
+
+// Can the tensor-core path take this problem?  (candidate capacity `cap` rows form epoch 0)
+static bool gemm_eligible(const wb_index* h, int64_t nrows, int64_t nq, int k, int* cap_out) {
+    if (env_int("WB_GEMM", 1) == 0) return false;
+    if (nq < env_int("WB_GEMM_MIN_NQ", 9)) return false;
+    if (nrows >= ((int64_t)1 << 31) - 256) return false;  // TMA coordinates are int32
+    int64_t cap = std::min<int64_t>(4096, std::max<int64_t>(256, ((nrows / 64) + 127) / 128 * 128));
+    if (cap < 2 * (int64_t)k || nrows < 4 * cap) return false;
+    *cap_out = (int)cap;
+    return true;
+}
+
+static int run_flat_gemm(wb_index* h, const float* rows, int64_t nrows, const float* q_ld, int64_t nq, int k, int cap,
+                         const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed, bool* overflowed) {
+    const int ld = h->ld;
+    const int nchunks = (ld + kGemmBK - 1) / kGemmBK;
+    const int nqb = (int)((nq + kGemmBN - 1) / kGemmBN);
+    const int kstride = k + cap;
+    TRY(h->gimg.ensure((size_t)nqb * nchunks * kGemmBBytes));
+    TRY(h->gkeys.ensure((size_t)nq * kstride * sizeof(uint64_t)));
+    TRY(h->gstate.ensure((size_t)nqb * kGemmBN * 4 + (size_t)nq * 4 + 64));
+    float* thr = h->gstate.as<float>();
+    int* cnt = reinterpret_cast<int*>(thr + (size_t)nqb * kGemmBN);
+    int* overflow = cnt + nq;
+    uint64_t* keys = h->gkeys.as<uint64_t>();
+    {
+        const int64_t n1 = std::max<int64_t>((int64_t)nqb * kGemmBN, nq * (int64_t)k);
+        init_gemm_state_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(thr, (int)nq, nqb * kGemmBN, cnt, keys, k,
+                                                                            kstride, overflow);
+        CK(cudaGetLastError());
+        const int64_t n2 = (int64_t)nqb * nchunks * 8 * kGemmBN;
+        split_queries_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb,
+                                                                          h->gimg.as<float>());
+        CK(cudaGetLastError());
+        h->launches += 2;
+    }
+    PFN_encodeTiled encode = nullptr;
+    TRY(get_tensormap_encoder(&encode));
+    CUtensorMap tmap;
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)nrows};
+        cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+        cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)kGemmBM};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)rows, gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    }
+    static thread_local bool attr_done[64] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_done[dev]) {
+        CK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+        if (dev < 64) attr_done[dev] = true;
+    }
+    TRY(merge_smem_optin<true>());
+    static thread_local bool cattr_done[64] = {};
+    if (dev >= 64 || !cattr_done[dev]) {
+        CK(cudaFuncSetAttribute(compact_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        if (dev < 64) cattr_done[dev] = true;
+    }
+    GemmParams g{};
+    g.nchunks = nchunks;
+    g.nq = (int)nq;
+    g.nqb = nqb;
+    g.bimg = h->gimg.as<float>();
+    g.thr = thr;
+    g.keys = keys;
+    g.cnt = cnt;
+    g.overflow = overflow;
+    g.k = k;
+    g.cap = cap;
+    g.kstride = kstride;
+    CompactParams c{};
+    c.k = k;
+    c.cap = cap;
+    c.kstride = kstride;
+    {
+        const int64_t mmax = (int64_t)k + cap;
+        const int full = pow2_ceil(k + 2 * kMergeThreads);
+        c.S = mmax <= full ? pow2_ceil((int)mmax) : full;
+    }
+    c.keys = keys;
+    c.cnt = cnt;
+    c.thr = thr;
+    c.ids = ids;
+    const double growth = std::min(3.0, std::max(0.25, (double)cap / (4.0 * k)));
+    const int evs = (int)(h->ev_count % wb_index::kEvRing);
+    if (timed && h->timing) CK(cudaEventRecord(h->ev0[evs], st));
+    int64_t r0 = 0;
+    while (r0 < nrows) {
+        int64_t len = r0 == 0 ? cap : (int64_t)((double)r0 * growth);
+        len = std::max<int64_t>(kGemmBM, (len + kGemmBM - 1) / kGemmBM * kGemmBM);
+        const int64_t r1 = std::min(nrows, r0 + len);
+        g.row_begin = r0;
+        g.row_end = r1;
+        const int64_t nwork = ((r1 - r0 + kGemmBM - 1) / kGemmBM) * nqb;
+        const unsigned grid = (unsigned)std::min<int64_t>(nwork, h->sm_count);
+        gemm_topk_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
+        CK(cudaGetLastError());
+        const bool last = r1 >= nrows;
+        c.D = last ? D : nullptr;
+        c.I = last ? I : nullptr;
+        compact_topk_kernel<<<(unsigned)nq, kMergeThreads, (size_t)c.S * 8, st>>>(c);
+        CK(cudaGetLastError());
+        h->launches += 2;
+        h->gemm_launches++;
+        r0 = r1;
+    }
+    if (timed && h->timing) {
+        CK(cudaEventRecord(h->ev1[evs], st));
+        h->ev_count++;
+    }
+    int ovf = 0;
+    CK(cudaMemcpyAsync(&ovf, overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *overflowed = ovf != 0;
+    return 0;
+}
+
+static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const float* q_dev, int64_t nq, int k,
+                         const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed);
+
+// Exhaustive top-k, any batch size: tensor cores (K2) when the batch is big enough, else the
+// bandwidth-bound CUDA-core scan (K1).  A candidate-list overflow in K2 (adversarially ordered data)
+// is repaired by re-running the batch through K1.
+static int run_flat_any(wb_index* h, const float* rows, int64_t nrows, const float* q_dev, int64_t nq, int k,
+                        const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed) {
+    int cap = 0;
+    if (gemm_eligible(h, nrows, nq, k, &cap)) {
+        const int64_t max_q = 65536;  // bounds the candidate buffers
+        bool any_overflow = false;
+        for (int64_t q0 = 0; q0 < nq; q0 += max_q) {
+            const int64_t nqc = std::min(max_q, nq - q0);
+            bool ovf = false;
+            TRY(run_flat_gemm(h, rows, nrows, q_dev + (size_t)q0 * h->ld, nqc, k, cap, ids, D + (size_t)q0 * k,
+                              I + (size_t)q0 * k, st, timed, &ovf));
+            any_overflow |= ovf;
+        }
+        if (!any_overflow) return 0;
+        h->gemm_fallbacks++;
+    }
+    return run_flat_scan(h, rows, nrows, q_dev, nq, k, ids, D, I, st, timed);
+}
+
 // ---- CSR inverted lists (host counting sort; insertion order kept inside each list) ---------
 static int build_csr_host(const int32_t* assign_dev, int64_t n, int64_t nlist, std::vector<uint32_t>& perm,
                           std::vector<int64_t>& off, cudaStream_t st) {
@@ -465,7 +636,7 @@ static int assign_rows(wb_index* h, const float* x_dev, int64_t n, int32_t* assi
     TRY(h->pD.ensure((size_t)n * sizeof(float)));
     TRY(h->pI.ensure((size_t)n * sizeof(int64_t)));
     float* D = best_out ? best_out : h->pD.as<float>();
-    TRY(run_flat_scan(h, h->centroids, h->nlist, x_dev, n, 1, nullptr, D, h->pI.as<int64_t>(), st, false));
+    TRY(run_flat_any(h, h->centroids, h->nlist, x_dev, n, 1, nullptr, D, h->pI.as<int64_t>(), st, false));
     i64_to_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pI.as<int64_t>(), assign_out, n);
     CK(cudaGetLastError());
     h->launches++;
@@ -534,13 +705,13 @@ extern "C" int wb_ivf_add_preassigned(wb_index* h, int64_t n, const float* x_hos
 // ---- search --------------------------------------------------------------------------------
 static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld] */, int64_t k, int64_t nprobe, float* D,
                            int64_t* I, cudaStream_t st) {
-    if (!h->ivf) return run_flat_scan(h, h->rows, h->n, q_ld, nq, (int)k, h->ids, D, I, st, true);
+    if (!h->ivf) return run_flat_any(h, h->rows, h->n, q_ld, nq, (int)k, h->ids, D, I, st, true);
     if (!h->trained) return fail("IndexIVFFlat is not trained");
     int np = (int)std::min<int64_t>(std::max<int64_t>(nprobe, 1), std::min<int64_t>(h->nlist, WB_MAX_K));
     // K4: coarse quantizer = exhaustive scan of the centroids, top-nprobe
     TRY(h->pD.ensure((size_t)nq * np * sizeof(float)));
     TRY(h->pI.ensure((size_t)nq * np * sizeof(int64_t)));
-    TRY(run_flat_scan(h, h->centroids, h->nlist, q_ld, nq, np, nullptr, h->pD.as<float>(), h->pI.as<int64_t>(), st, false));
+    TRY(run_flat_any(h, h->centroids, h->nlist, q_ld, nq, np, nullptr, h->pD.as<float>(), h->pI.as<int64_t>(), st, false));
     if (h->csr_dirty) {
         if (st != h->stream) CK(cudaStreamSynchronize(st));
         TRY(ensure_csr(h));

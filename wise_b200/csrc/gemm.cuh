@@ -1,0 +1,362 @@
+// gemm.cuh - K2 flat_gemm_topk: batched exhaustive inner product on the 5th-gen tensor cores
+// (tcgen05.mma kind::tf32, 3xTF32 split for fp32 accuracy) with a fused top-k filter epilogue.
+//
+// Replaces faiss exhaustive_inner_product_blas (sgemm tiles + heap/reservoir add_results)
+// [faiss-upstream], the n >= 20 branch of knn_inner_product reached from
+// /root/reference/src/index/feature_search_index.py:113, and serves the same contraction for the
+// IVF coarse quantizer / add-time assignment and the k-means assignment (k = 1).
+//
+// S[row, q] = sum_t X[row, t] * Q[q, t],  X = database rows (A operand, M = 128 rows per tile),
+// Q = a block of BN = 128 queries (B operand), both K-major.  x*y ~= xh*yh + xh*yl + xl*yh with
+// xh = tf32-truncated x, xl = x - xh (exact in fp32): three MMAs per k-step into one fp32
+// accumulator in TMEM; the dropped xl*yl term is < 2^-20 relative.
+//
+// One persistent CTA per SM, 12 warps:
+//   warp 0      producer : per 32-float k-chunk one 2-D TMA load of the raw fp32 row tile
+//                          (128 x 128 B, SWIZZLE_128B) + one bulk copy of the pre-split query image
+//   warps 4-7   transform: thread = row; reads its 128 B of the swizzled tile (conflict-free),
+//                          splits hi/lo and stores both straight into TENSOR MEMORY (tcgen05.st):
+//                          the A operand never goes back to shared memory
+//   warp 1      MMA      : one thread issues 12 tcgen05.mma (A from TMEM, B from a no-swizzle K-major
+//                          shared-memory descriptor) per chunk; tcgen05.commit releases the stage
+//   warps 8-11  epilogue : tcgen05.ld of the finished 128x128 fp32 tile (double-buffered in TMEM, so
+//                          it overlaps the next tile's MMAs); a score survives only if it beats the
+//                          query's current k-th best; survivors are appended to a per-query
+//                          candidate list in global memory (warp-aggregated atomics)
+//   warp 2      TMEM allocator.
+// Scores never go to HBM.  The host runs the database in growing "epochs"; between epochs
+// compact_topk_kernel (merge.cuh) folds the candidates into the per-query top-k and tightens the
+// thresholds, so the expected number of survivors per epoch stays ~3k per query.
+// Algorithmic work: 2*nq*N*d flop (the split issues 3x that on the tensor pipe).
+#pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
+
+#include "common.cuh"
+
+namespace wb {
+
+constexpr int kGemmBM = 128;      // database rows per tile (UMMA M)
+constexpr int kGemmBN = 128;      // queries per block (UMMA N)
+constexpr int kGemmBK = 32;       // floats per k-chunk (128 B = one swizzle-128B row)
+constexpr int kGemmStages = 4;    // shared-memory ring == TMEM A-operand ring
+constexpr int kGemmThreads = 384;
+constexpr int kGemmABytes = kGemmBM * kGemmBK * 4;       // 16 KB raw row tile
+constexpr int kGemmBBytes = 2 * kGemmBN * kGemmBK * 4;   // 32 KB: hi image + lo image
+constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
+constexpr int kTmemCols = 512;
+constexpr int kTmemAOff = 2 * kGemmBN;                   // D0 | D1 | A ring (64 columns per stage)
+constexpr int kBarEpilogue = 2;
+
+struct GemmParams {
+    int64_t row_begin, row_end;   // this epoch's rows (row_begin is a multiple of 128)
+    int nchunks;                  // ceil(ld / 32)
+    int nq;                       // real queries
+    int nqb;                      // query blocks of 128
+    const float* bimg;            // [nqb][nchunks][2][8][128][4] pre-split query images
+    const float* thr;             // [nqb*128] current k-th best score per query (+inf for padding)
+    uint64_t* keys;               // [nq][kstride]: [0,k) current top-k, [k, k+cap) candidates
+    int* cnt;                     // [nq] candidates appended so far
+    int* overflow;                // set when a candidate list ran out of room
+    int k, cap, kstride;
+};
+
+// ---- tcgen05 / TMA PTX -----------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// K-major, no-swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=0 [61,64)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+// cute::UMMA::InstrDescriptor: c=F32 [4,6) | a=TF32 [7,10) | b=TF32 [10,13) | K-major A,B | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define WB_R32(v) \
+    v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], v[16], \
+        v[17], v[18], v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// ---- query pre-split: fp32 queries -> (hi, lo) images in the UMMA no-swizzle K-major layout ----
+// image[qb][chunk][half][k16 = 0..7][n = 0..127][4 floats]: a core matrix (8 queries x 16 B) is 128
+// contiguous bytes, SBO = 128 B between 8-query groups, LBO = 2048 B between 16-byte k columns.
+__global__ void split_queries_kernel(const float* q, int nq, int ld, int nchunks, int nqb, float* img) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one float4 per thread
+    const int64_t total = (int64_t)nqb * nchunks * 8 * kGemmBN;
+    if (i >= total) return;
+    const int n = (int)(i % kGemmBN);
+    const int k16 = (int)((i / kGemmBN) % 8);
+    const int chunk = (int)((i / (kGemmBN * 8)) % nchunks);
+    const int qb = (int)(i / ((int64_t)kGemmBN * 8 * nchunks));
+    const int qi = qb * kGemmBN + n;
+    const int col = chunk * kGemmBK + k16 * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (qi < nq) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (col + e < ld) v[e] = q[(size_t)qi * ld + col + e];
+    }
+    float hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        hi[e] = __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u);
+        lo[e] = v[e] - hi[e];
+    }
+    const size_t base = ((size_t)(qb * nchunks + chunk) * 2) * (8 * kGemmBN * 4);
+    const size_t off = ((size_t)k16 * kGemmBN + n) * 4;
+    *reinterpret_cast<float4*>(img + base + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(img + base + 8 * kGemmBN * 4 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+__global__ void init_gemm_state_kernel(float* thr, int nq, int nq_pad, int* cnt, uint64_t* keys, int k, int kstride,
+                                       int* overflow) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nq_pad) thr[i] = i < nq ? -INFINITY : INFINITY;
+    if (i < nq) cnt[i] = 0;
+    if (i == 0) *overflow = 0;
+    if (i < (int64_t)nq * k) keys[(i / k) * kstride + (i % k)] = 0ull;
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_gemm[];
+    // [stage s: A raw 16 KB | B image 32 KB] x 4, then barriers and small state.  SWIZZLE_128B needs the
+    // stage bases 1024-byte aligned: align by hand (the launch reserves 1 KB of slack).
+    unsigned char* stages = smem_gemm + ((1024u - (smem_u32(smem_gemm) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(stages + kGemmStages * kGemmStageBytes);
+    uint64_t* empty = full + kGemmStages;
+    uint64_t* a_full = empty + kGemmStages;
+    uint64_t* d_full = a_full + kGemmStages;
+    uint64_t* d_empty = d_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+    float* thr_s = reinterpret_cast<float*>(tmem_slot + 2);  // [2][128]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles = (p.row_end - p.row_begin + kGemmBM - 1) / kGemmBM;
+    const int64_t nwork = ntiles * p.nqb;
+
+    if (tid == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 5);   // 4 transform warps + 1 tcgen05.commit
+            mbar_init(&a_full[s], 4);  // 4 transform warps
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&d_full[b], 1);
+            mbar_init(&d_empty[b], 4);  // 4 epilogue warps
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== producer ===============================================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int64_t tile = w / p.nqb;
+                const int qb = (int)(w - tile * p.nqb);
+                const int row0 = (int)(p.row_begin + tile * kGemmBM);
+                const float* bsrc = p.bimg + (size_t)qb * p.nchunks * (kGemmBBytes / 4);
+                for (int c = 0; c < p.nchunks; ++c) {
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    unsigned char* st = stages + (size_t)s * kGemmStageBytes;
+                    mbar_arrive_expect_tx(&full[s], kGemmStageBytes);
+                    tma_load_2d(st, &tmap, c * kGemmBK, row0, &full[s]);
+                    bulk_g2s(st + kGemmABytes, bsrc + (size_t)c * (kGemmBBytes / 4), kGemmBBytes, &full[s]);
+                    if (++s == kGemmStages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer =============================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(kGemmBM, kGemmBN);
+            int s = 0;
+            uint32_t ph = 0;
+            int buf = 0;
+            uint32_t dph = 0;
+            for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+                mbar_wait(&d_empty[buf], dph ^ 1u);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kGemmBN);
+                for (int c = 0; c < p.nchunks; ++c) {
+                    mbar_wait(&full[s], ph);    // B image landed
+                    mbar_wait(&a_full[s], ph);  // A hi/lo written to TMEM
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_u32(stages + (size_t)s * kGemmStageBytes + kGemmABytes);
+                    const uint32_t b_lo = b_hi + kGemmBBytes / 2;
+                    const uint32_t a_hi = tmem_base + (uint32_t)(kTmemAOff + s * 64);
+                    const uint32_t a_lo = a_hi + 32;
+#pragma unroll
+                    for (int j = 0; j < kGemmBK / 8; ++j) {
+                        // one k-step = 8 tf32 = two 16-byte k columns: LBO = 2048 B, SBO = 128 B
+                        const uint64_t dh = umma_smem_desc(b_hi + j * 4096, 2048, 128);
+                        const uint64_t dl = umma_smem_desc(b_lo + j * 4096, 2048, 128);
+                        umma_tf32_ts(d_tmem, a_hi + j * 8, dh, idesc, (c | j) != 0);
+                        umma_tf32_ts(d_tmem, a_hi + j * 8, dl, idesc, 1);
+                        umma_tf32_ts(d_tmem, a_lo + j * 8, dh, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);  // stage (smem B + TMEM A) is free once these MMAs retire
+                    if (++s == kGemmStages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(&d_full[buf]);
+                if (++buf == 2) { buf = 0; dph ^= 1u; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // =============================== transform: fp32 -> (hi, lo) in TMEM ======================
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait(&full[s], ph);
+                const unsigned char* a_raw = stages + (size_t)s * kGemmStageBytes + (size_t)r * 128;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const float4 v = *reinterpret_cast<const float4*>(a_raw + ((ch ^ (r & 7)) << 4));  // SWIZZLE_128B
+                    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t h = __float_as_uint(x[e]) & 0xFFFFE000u;
+                        hi[ch * 4 + e] = h;
+                        lo[ch * 4 + e] = __float_as_uint(x[e] - __uint_as_float(h));
+                    }
+                }
+                const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kTmemAOff + s * 64);
+                tmem_st32(ta, hi);
+                tmem_st32(ta + 32, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&a_full[s]);
+                    mbar_arrive(&empty[s]);  // raw tile consumed
+                }
+                if (++s == kGemmStages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp >= 8) {
+        // =============================== epilogue: threshold filter ================================
+        const int quarter = warp & 3;
+        const int etid = tid - 8 * 32;
+        int buf = 0;
+        uint32_t dph = 0;
+        for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+            const int64_t tile = w / p.nqb;
+            const int qb = (int)(w - tile * p.nqb);
+            const int64_t row = p.row_begin + tile * kGemmBM + quarter * 32 + lane;
+            const bool row_ok = row < p.row_end;
+            thr_s[buf * kGemmBN + etid] = p.thr[qb * kGemmBN + etid];
+            named_bar_sync(kBarEpilogue, 128);
+            mbar_wait(&d_full[buf], dph);
+            tc_fence_after();
+            const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kGemmBN);
+#pragma unroll 1
+            for (int cb = 0; cb < kGemmBN / 32; ++cb) {
+                uint32_t v[32];
+                tmem_ld32(td + cb * 32, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float sc = __uint_as_float(v[j]);
+                    const bool pass = row_ok && sc > thr_s[buf * kGemmBN + cb * 32 + j];
+                    const unsigned m = __ballot_sync(0xffffffffu, pass);
+                    if (m) {
+                        const int qi = qb * kGemmBN + cb * 32 + j;  // < nq: padded queries have thr = +inf
+                        int base = 0;
+                        if (lane == (__ffs(m) - 1)) base = atomicAdd(&p.cnt[qi], __popc(m));
+                        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                        if (pass) {
+                            const int slot = base + __popc(m & ((1u << lane) - 1));
+                            if (slot < p.cap) p.keys[(size_t)qi * p.kstride + p.k + slot] = make_key(sc, (uint32_t)row);
+                            else *p.overflow = 1;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[buf]);
+            named_bar_sync(kBarEpilogue, 128);  // thr_s[buf] may be rewritten two tiles later
+            if (++buf == 2) { buf = 0; dph ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+constexpr size_t kGemmSmemBytes =
+    1024 + (size_t)kGemmStages * kGemmStageBytes + (3 * kGemmStages + 4) * 8 + 16 + 2 * kGemmBN * 4;
+
+}  // namespace wb

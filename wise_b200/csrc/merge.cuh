@@ -38,21 +38,16 @@ __device__ __forceinline__ uint64_t merge_load(const MergeParams& p, int64_t q, 
     }
 }
 
-// buf = [ best k (sorted) | queue ].  Round 0 sorts the first S candidates; after that a candidate
-// is queued only if it beats the current k-th best, so almost everything dies on one compare and
-// the buffer is re-sorted only when the queue could overflow.
-template <bool FROM_KEYS>
-__global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergeParams p) {
-    extern __shared__ __align__(16) unsigned char smem_merge[];
-    uint64_t* buf = reinterpret_cast<uint64_t*>(smem_merge);
-    __shared__ int cnt;
+// Block-level top-k of M candidates produced by load(i), i in [0, M): leaves the k best keys sorted
+// (descending) in buf[0, k).  buf = [ best k | queue ]: round 0 sorts the first S candidates; after
+// that a candidate is queued only if it beats the current k-th best, so almost everything dies on
+// one compare and the buffer is re-sorted only when the queue could overflow.
+template <class Load>
+__device__ __forceinline__ void block_select_topk(uint64_t* buf, int S, int k, int64_t M, Load load, int* cnt) {
     const int tid = threadIdx.x;
-    const int64_t q = blockIdx.x;
-    const int k = p.k, S = p.S;
-    const int64_t M = p.nparts * (int64_t)k;
     const int first = (int)min((int64_t)S, M);
-    for (int i = tid; i < S; i += kMergeThreads) buf[i] = i < first ? merge_load<FROM_KEYS>(p, q, M, i) : 0ull;
-    if (tid == 0) cnt = 0;
+    for (int i = tid; i < S; i += kMergeThreads) buf[i] = i < first ? load((int64_t)i) : 0ull;
+    if (tid == 0) *cnt = 0;
     __syncthreads();
     bitonic_sort_desc<kMergeThreads>(buf, S, 1, tid, -1);
     const int qcap = S - k;
@@ -62,25 +57,38 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
         __syncthreads();
         const uint64_t thr = buf[k - 1];
         const int64_t c = base + tid;
-        const uint64_t key = c < M ? merge_load<FROM_KEYS>(p, q, M, c) : 0ull;
+        const uint64_t key = c < M ? load(c) : 0ull;
         const bool pass = key > thr;  // also rejects empty slots (0)
         const unsigned m = __ballot_sync(0xffffffffu, pass);
         if (m) {
             int slot0 = 0;
-            if ((tid & 31) == 0) slot0 = atomicAdd(&cnt, __popc(m));
+            if ((tid & 31) == 0) slot0 = atomicAdd(cnt, __popc(m));
             slot0 = __shfl_sync(0xffffffffu, slot0, 0);
             if (pass) buf[k + slot0 + __popc(m & ((1u << (tid & 31)) - 1))] = key;
         }
         __syncthreads();
-        if (cnt > qcap - kMergeThreads) {  // uniform: cnt is read after the barrier
+        if (*cnt > qcap - kMergeThreads) {  // uniform: cnt is read after the barrier
             bitonic_sort_desc<kMergeThreads>(buf, S, 1, tid, -1);
             for (int i = k + tid; i < S; i += kMergeThreads) buf[i] = 0ull;
-            if (tid == 0) cnt = 0;
+            if (tid == 0) *cnt = 0;
             __syncthreads();
         }
     }
     __syncthreads();
-    if (cnt > 0) bitonic_sort_desc<kMergeThreads>(buf, S, 1, tid, -1);
+    if (*cnt > 0) bitonic_sort_desc<kMergeThreads>(buf, S, 1, tid, -1);
+    __syncthreads();
+}
+
+template <bool FROM_KEYS>
+__global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_merge[];
+    uint64_t* buf = reinterpret_cast<uint64_t*>(smem_merge);
+    __shared__ int cnt;
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    const int k = p.k;
+    const int64_t M = p.nparts * (int64_t)k;
+    block_select_topk(buf, p.S, k, M, [&](int64_t c) { return merge_load<FROM_KEYS>(p, q, M, c); }, &cnt);
     for (int j = tid; j < k; j += kMergeThreads) {
         const uint64_t key = buf[j];
         float d = -FLT_MAX;
@@ -97,6 +105,44 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
         }
         p.D[q * k + j] = d;
         p.I[q * k + j] = id;
+    }
+}
+
+// K2 epoch boundary: fold the candidates a query collected during the epoch into its top-k,
+// tighten its threshold, reset its candidate counter; on the last epoch also emit (D, I).
+struct CompactParams {
+    int k, cap, kstride, S;
+    uint64_t* keys;   // [nq][kstride]: [0,k) top-k so far (sorted), [k, k+cap) candidates
+    int* cnt;         // [nq]
+    float* thr;       // [nq_pad]
+    const int64_t* ids;
+    float* D;         // null unless this is the last epoch
+    int64_t* I;
+};
+
+__global__ void __launch_bounds__(kMergeThreads) compact_topk_kernel(const CompactParams p) {
+    extern __shared__ __align__(16) unsigned char smem_merge[];
+    uint64_t* buf = reinterpret_cast<uint64_t*>(smem_merge);
+    __shared__ int cnt;
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    const int k = p.k;
+    uint64_t* base = p.keys + q * p.kstride;
+    const int64_t M = k + min(p.cnt[q], p.cap);
+    block_select_topk(buf, p.S, k, M, [&](int64_t c) { return base[c]; }, &cnt);
+    for (int j = tid; j < k; j += kMergeThreads) {
+        const uint64_t key = buf[j];
+        base[j] = key;
+        if (p.D) {
+            p.D[q * k + j] = key ? key_score(key) : -FLT_MAX;
+            const uint32_t pos = key_pos(key);
+            p.I[q * k + j] = key ? (p.ids ? p.ids[pos] : (int64_t)pos) : -1;
+        }
+    }
+    if (tid == 0) {
+        const uint64_t kth = buf[k - 1];
+        p.thr[q] = kth ? key_score(kth) : -INFINITY;
+        p.cnt[q] = 0;
     }
 }
 
