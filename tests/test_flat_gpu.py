@@ -225,3 +225,65 @@ def test_large_scan_properties_2m_x_768(faiss):
     for j in range(nq):
         better = samp_h[s[:, j] > D[j, -1] + 2e-6]
         assert set(better.tolist()) <= set(I[j].tolist())
+
+
+# ---- K2: tensor-core path (batches >= 9 queries) -------------------------------------------------
+def _gemm_stats(idx):
+    from wise_b200 import _capi
+    a, b = C.c_int64(), C.c_int64()
+    _capi.lib().wb_gemm_stats(idx._h, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+@pytest.mark.parametrize("n,d,nq,k,clustered", [
+    (40000, 768, 16, 10, False), (40000, 768, 128, 10, False), (100000, 512, 200, 100, False),
+    (50000, 100, 33, 5, False), (131072, 768, 300, 100, True), (70001, 1024, 64, 50, False),
+    (300000, 64, 1000, 10, False), (60000, 70, 129, 100, True), (200000, 768, 1024, 100, True)])
+def test_gemm_path_matches_oracle(faiss, n, d, nq, k, clustered):
+    """3xTF32 on tcgen05: scores within 1e-5 of the fp64 oracle (observed ~1.5e-6), ids identical outside
+    near-tie bands; the band is widened to 4e-6 here because the tensor-core accumulation noise is ~1.5e-6."""
+    xb = O.clustered_unit(n, d, 64, 1) if clustered else O.unit_gaussian(n, d, 100)
+    xq = O.clustered_unit(nq, d, 64, 2) if clustered else O.unit_gaussian(nq, d, 200)
+    ids = np.arange(n, dtype=np.int64) * 3 + 1
+    idx = _flat(faiss, xb, ids)
+    D, I = idx.search(xq, k)
+    epochs, fallbacks = _gemm_stats(idx)
+    assert epochs >= 3 and fallbacks == 0, "the tensor-core path must have served this batch"
+    Dr, Ir = O.flat_search(xb, xq, k, ids)
+    O.compare_topk(D, I, Dr, Ir, band=4e-6)
+    # the CUDA-core path on the same index gives the same members (different kernel, same contract)
+    D8, I8 = idx.search(xq[:8], k)
+    O.compare_topk(D8, I8, Dr[:8], Ir[:8])
+
+
+def test_gemm_path_duplicates_tie_rule(faiss):
+    n, d, k = 60000, 256, 20
+    xb = O.unit_gaussian(n, d, 5)
+    xb[30000:30500] = xb[:500]
+    xq = np.concatenate([O.unit_gaussian(28, d, 6), xb[100:104]])
+    idx = _flat(faiss, xb)
+    D, I = idx.search(xq, k)
+    assert _gemm_stats(idx)[0] > 0
+    O.compare_topk(D, I, *O.flat_search(xb, xq, k), band=4e-6)
+    for j in range(4):  # exact duplicates: bit-identical scores, lowest position first
+        assert I[28 + j, 0] == 100 + j and I[28 + j, 1] == 30100 + j and D[28 + j, 0] == D[28 + j, 1]
+
+
+def test_gemm_overflow_falls_back_exactly(faiss):
+    """Adversarial order: rows sorted by ascending score for every query, so every row beats the running
+    threshold and the candidate lists overflow; the batch is then repaired by the CUDA-core scan."""
+    n, d, k = 120000, 64, 10
+    rng = np.random.default_rng(0)
+    base = O.unit_gaussian(1, d, 1)[0]
+    t = np.linspace(-0.9, 0.9, n).astype(np.float32)  # score of row i against `base` grows with i
+    noise = O.unit_gaussian(n, d, 2)
+    noise -= (noise @ base)[:, None] * base[None, :]
+    noise /= np.linalg.norm(noise, axis=1, keepdims=True)
+    xb = (t[:, None] * base[None, :] + np.sqrt(1 - t[:, None] ** 2) * noise).astype(np.float32)
+    xq = np.repeat(base[None, :], 16, axis=0) + 1e-3 * rng.standard_normal((16, d)).astype(np.float32)
+    xq /= np.linalg.norm(xq, axis=1, keepdims=True)
+    idx = _flat(faiss, xb)
+    D, I = idx.search(xq.astype(np.float32), k)
+    epochs, fallbacks = _gemm_stats(idx)
+    assert epochs > 0 and fallbacks == 1
+    O.compare_topk(D, I, *O.flat_search(xb, xq.astype(np.float32), k))
