@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwiseb200.so")
+LIB_PATH = os.environ.get("WISE_B200_LIB") or os.path.join(_HERE, "libwiseb200.so")
 
 WB_MAX_K = 2048
 

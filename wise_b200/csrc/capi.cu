@@ -458,8 +458,13 @@ static bool gemm_eligible(const wb_index* h, int64_t nrows, int64_t nq, int k, i
     return true;
 }
 
-static int run_flat_gemm(wb_index* h, const float* rows, int64_t nrows, const float* q_ld, int64_t nq, int k, int cap,
+template <int BN>
+static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const float* q_ld, int64_t nq, int k, int cap,
                          const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed, bool* overflowed) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int kGemmBN = BN;
+    constexpr int kGemmBBytes = Cfg::kBBytes;
+    constexpr size_t kGemmSmemBytes = Cfg::kSmemBytes;
     const int ld = h->ld;
     const int nchunks = (ld + kGemmBK - 1) / kGemmBK;
     const int nqb = (int)((nq + kGemmBN - 1) / kGemmBN);
@@ -477,7 +482,7 @@ static int run_flat_gemm(wb_index* h, const float* rows, int64_t nrows, const fl
                                                                             kstride, overflow);
         CK(cudaGetLastError());
         const int64_t n2 = (int64_t)nqb * nchunks * 8 * kGemmBN;
-        split_queries_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb,
+        split_queries_kernel<BN><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb,
                                                                           h->gimg.as<float>());
         CK(cudaGetLastError());
         h->launches += 2;
@@ -499,7 +504,7 @@ static int run_flat_gemm(wb_index* h, const float* rows, int64_t nrows, const fl
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_done[dev]) {
-        CK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+        CK(cudaFuncSetAttribute(gemm_topk_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
         if (dev < 64) attr_done[dev] = true;
     }
     TRY(merge_smem_optin<true>());
@@ -513,6 +518,7 @@ static int run_flat_gemm(wb_index* h, const float* rows, int64_t nrows, const fl
     g.nq = (int)nq;
     g.nqb = nqb;
     g.bimg = h->gimg.as<float>();
+    g.debug_terms = env_int("WB_GEMM_DEBUG_TERMS", 3);
     g.thr = thr;
     g.keys = keys;
     g.cnt = cnt;
@@ -545,7 +551,7 @@ static int run_flat_gemm(wb_index* h, const float* rows, int64_t nrows, const fl
         g.row_end = r1;
         const int64_t nwork = ((r1 - r0 + kGemmBM - 1) / kGemmBM) * nqb;
         const unsigned grid = (unsigned)std::min<int64_t>(nwork, h->sm_count);
-        gemm_topk_kernel<<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
+        gemm_topk_kernel<BN><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
         CK(cudaGetLastError());
         const bool last = r1 >= nrows;
         c.D = last ? D : nullptr;
@@ -565,6 +571,15 @@ static int run_flat_gemm(wb_index* h, const float* rows, int64_t nrows, const fl
     CK(cudaStreamSynchronize(st));
     *overflowed = ovf != 0;
     return 0;
+}
+
+static int run_flat_gemm(wb_index* h, const float* rows, int64_t nrows, const float* q_ld, int64_t nq, int k, int cap,
+                         const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed, bool* overflowed) {
+    const int bn_max = env_int("WB_GEMM_BN", 128);
+    if (nq <= 32 && bn_max >= 32) return run_flat_gemm_t<32>(h, rows, nrows, q_ld, nq, k, cap, ids, D, I, st, timed, overflowed);
+    if ((nq <= 64 && bn_max >= 64) || bn_max < 128)
+        return run_flat_gemm_t<64>(h, rows, nrows, q_ld, nq, k, cap, ids, D, I, st, timed, overflowed);
+    return run_flat_gemm_t<128>(h, rows, nrows, q_ld, nq, k, cap, ids, D, I, st, timed, overflowed);
 }
 
 static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const float* q_dev, int64_t nq, int k,

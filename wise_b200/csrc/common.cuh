@@ -79,6 +79,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// One lane of a fully converged warp.  Code guarded by this predicate is known to the compiler to run
+// in exactly one thread, so warp-uniform instructions (UTCHMMA, UTMALDG, UTCBAR) get their operands in
+// uniform registers directly; a plain `if (lane == 0)` makes nvcc wrap every such instruction in an
+// ELECT / BRA.U.ANY serialisation loop (~100 cycles per tcgen05.mma - measured, profiles/r01).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, px;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- named barriers (sub-CTA sync among the consumer warps) -----------------------------------
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

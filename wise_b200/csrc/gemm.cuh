@@ -11,10 +11,11 @@
 // xh = tf32-truncated x, xl = x - xh (exact in fp32): three MMAs per k-step into one fp32
 // accumulator in TMEM; the dropped xl*yl term is < 2^-20 relative.
 //
-// One persistent CTA per SM, 12 warps:
-//   warp 0      producer : per 32-float k-chunk one 2-D TMA load of the raw fp32 row tile
-//                          (128 x 128 B, SWIZZLE_128B) + one bulk copy of the pre-split query image
-//   warps 4-7   transform: thread = row; reads its 128 B of the swizzled tile (conflict-free),
+// One persistent CTA per SM, 16 warps:
+//   warp 0      producer A: per 32-float k-chunk one 2-D TMA load of the raw fp32 row tile
+//                          (128 x 128 B, SWIZZLE_128B) into a deep ring freed by the transform warps
+//   warp 3      producer B: one bulk copy of the pre-split query image per chunk into the operand slots
+//   warps 4-7, 12-15 transform (two sets on alternate chunks): thread = row; reads its 128 B of the swizzled tile (conflict-free),
 //                          splits hi/lo and stores both straight into TENSOR MEMORY (tcgen05.st):
 //                          the A operand never goes back to shared memory
 //   warp 1      MMA      : one thread issues 12 tcgen05.mma (A from TMEM, B from a no-swizzle K-major
@@ -33,27 +34,47 @@
 
 #include "common.cuh"
 
+#ifndef WB_GEMM_ELECT_MMA
+#define WB_GEMM_ELECT_MMA 1
+#endif
+#ifndef WB_GEMM_ELECT_PROD
+#define WB_GEMM_ELECT_PROD 1
+#endif
+
 namespace wb {
 
 constexpr int kGemmBM = 128;      // database rows per tile (UMMA M)
-constexpr int kGemmBN = 128;      // queries per block (UMMA N)
 constexpr int kGemmBK = 32;       // floats per k-chunk (128 B = one swizzle-128B row)
-constexpr int kGemmStages = 4;    // shared-memory ring == TMEM A-operand ring
-constexpr int kGemmThreads = 384;
+constexpr int kGemmThreads = 512;
 constexpr int kGemmABytes = kGemmBM * kGemmBK * 4;       // 16 KB raw row tile
-constexpr int kGemmBBytes = 2 * kGemmBN * kGemmBK * 4;   // 32 KB: hi image + lo image
-constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
 constexpr int kTmemCols = 512;
-constexpr int kTmemAOff = 2 * kGemmBN;                   // D0 | D1 | A ring (64 columns per stage)
 constexpr int kBarEpilogue = 2;
+
+// Per query-block width BN (UMMA N = 32 / 64 / 128): small batches use a narrow block so the kernel
+// stays bound by the HBM stream of the rows instead of by padded MMAs and query-image traffic.
+template <int BN>
+struct GemmCfg {
+    static constexpr int kBBytes = 2 * BN * kGemmBK * 4;             // hi image + lo image of one k-chunk
+    static constexpr int kTmemAOff = 2 * BN;                          // TMEM: D0 | D1 | A ring (64 columns per slot)
+    // Ring 2 ("operand slots"): query image in shared memory + split A operand in TMEM; freed by tcgen05.commit.
+    static constexpr int kSlots = (kTmemCols - kTmemAOff) / 64;       // 4 / 6 / 7 for BN = 128 / 64 / 32
+    // Ring 1: raw fp32 row tiles straight from TMA; freed by the transform warps, so it can run far ahead of
+    // the MMAs - it is what keeps enough bytes in flight to cover the loaded HBM latency (~3.5 us).
+    static constexpr int kRawStages = (224 * 1024 - kSlots * kBBytes) / kGemmABytes;
+    static constexpr int kNumBars = 2 * kRawStages + 3 * kSlots + 4;
+    static constexpr size_t kSmemBytes =
+        1024 + (size_t)kRawStages * kGemmABytes + (size_t)kSlots * kBBytes + kNumBars * 8 + 16 + 2 * BN * 4;
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
 
 struct GemmParams {
     int64_t row_begin, row_end;   // this epoch's rows (row_begin is a multiple of 128)
     int nchunks;                  // ceil(ld / 32)
     int nq;                       // real queries
-    int nqb;                      // query blocks of 128
-    const float* bimg;            // [nqb][nchunks][2][8][128][4] pre-split query images
-    const float* thr;             // [nqb*128] current k-th best score per query (+inf for padding)
+    int nqb;                      // query blocks of BN queries
+    int debug_terms;              // timing experiments only: number of split terms issued (3 = correct)
+    const float* bimg;            // [nqb][nchunks][2][8][BN][4] pre-split query images
+    const float* thr;             // [nqb*BN] current k-th best score per query (+inf for padding)
     uint64_t* keys;               // [nq][kstride]: [0,k) current top-k, [k, k+cap) candidates
     int* cnt;                     // [nq] candidates appended so far
     int* overflow;                // set when a candidate list ran out of room
@@ -130,9 +151,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // ---- query pre-split: fp32 queries -> (hi, lo) images in the UMMA no-swizzle K-major layout ----
-// image[qb][chunk][half][k16 = 0..7][n = 0..127][4 floats]: a core matrix (8 queries x 16 B) is 128
-// contiguous bytes, SBO = 128 B between 8-query groups, LBO = 2048 B between 16-byte k columns.
+// image[qb][chunk][half][k16 = 0..7][n = 0..BN-1][4 floats]: a core matrix (8 queries x 16 B) is 128
+// contiguous bytes, SBO = 128 B between 8-query groups, LBO = BN*16 B between 16-byte k columns.
+template <int BN>
 __global__ void split_queries_kernel(const float* q, int nq, int ld, int nchunks, int nqb, float* img) {
+    constexpr int kGemmBN = BN;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one float4 per thread
     const int64_t total = (int64_t)nqb * nchunks * 8 * kGemmBN;
     if (i >= total) return;
@@ -170,29 +193,42 @@ __global__ void init_gemm_state_kernel(float* thr, int nq, int nq_pad, int* cnt,
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
+template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int kRaw = Cfg::kRawStages;
+    constexpr int kSlots = Cfg::kSlots;
+    constexpr int kBBytes = Cfg::kBBytes;
+    constexpr int kTmemAOff = Cfg::kTmemAOff;
     extern __shared__ __align__(1024) unsigned char smem_gemm[];
-    // [stage s: A raw 16 KB | B image 32 KB] x 4, then barriers and small state.  SWIZZLE_128B needs the
-    // stage bases 1024-byte aligned: align by hand (the launch reserves 1 KB of slack).
-    unsigned char* stages = smem_gemm + ((1024u - (smem_u32(smem_gemm) & 1023u)) & 1023u);
-    uint64_t* full = reinterpret_cast<uint64_t*>(stages + kGemmStages * kGemmStageBytes);
-    uint64_t* empty = full + kGemmStages;
-    uint64_t* a_full = empty + kGemmStages;
-    uint64_t* d_full = a_full + kGemmStages;
+    // [raw row tiles 16 KB x kRaw | query images kBBytes x kSlots | barriers | thresholds].  SWIZZLE_128B needs
+    // 1024-byte aligned tiles: align by hand (the launch reserves 1 KB of slack).
+    unsigned char* raw = smem_gemm + ((1024u - (smem_u32(smem_gemm) & 1023u)) & 1023u);
+    unsigned char* bimg_s = raw + (size_t)kRaw * kGemmABytes;
+    uint64_t* raw_full = reinterpret_cast<uint64_t*>(bimg_s + (size_t)kSlots * kBBytes);
+    uint64_t* raw_empty = raw_full + kRaw;
+    uint64_t* b_full = raw_empty + kRaw;
+    uint64_t* a_full = b_full + kSlots;
+    uint64_t* slot_empty = a_full + kSlots;
+    uint64_t* d_full = slot_empty + kSlots;
     uint64_t* d_empty = d_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
-    float* thr_s = reinterpret_cast<float*>(tmem_slot + 2);  // [2][128]
+    float* thr_s = reinterpret_cast<float*>(tmem_slot + 2);  // [2][BN]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (p.row_end - p.row_begin + kGemmBM - 1) / kGemmBM;
     const int64_t nwork = ntiles * p.nqb;
 
     if (tid == 0) {
-        for (int s = 0; s < kGemmStages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 5);   // 4 transform warps + 1 tcgen05.commit
-            mbar_init(&a_full[s], 4);  // 4 transform warps
+        for (int s = 0; s < kRaw; ++s) {
+            mbar_init(&raw_full[s], 1);
+            mbar_init(&raw_empty[s], 4);  // 4 transform warps
+        }
+        for (int s = 0; s < kSlots; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&a_full[s], 4);      // 4 transform warps
+            mbar_init(&slot_empty[s], 1);  // tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&d_full[b], 1);
@@ -212,29 +248,48 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // =============================== producer ===============================================
-        if (lane == 0) {
+        // =============================== producer A: raw row tiles (ring 1) =========================
+        {   // the whole warp runs the control flow (converged); one elected lane issues
             int s = 0;
             uint32_t ph = 0;
             for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
                 const int64_t tile = w / p.nqb;
-                const int qb = (int)(w - tile * p.nqb);
                 const int row0 = (int)(p.row_begin + tile * kGemmBM);
-                const float* bsrc = p.bimg + (size_t)qb * p.nchunks * (kGemmBBytes / 4);
                 for (int c = 0; c < p.nchunks; ++c) {
-                    mbar_wait(&empty[s], ph ^ 1u);
-                    unsigned char* st = stages + (size_t)s * kGemmStageBytes;
-                    mbar_arrive_expect_tx(&full[s], kGemmStageBytes);
-                    tma_load_2d(st, &tmap, c * kGemmBK, row0, &full[s]);
-                    bulk_g2s(st + kGemmABytes, bsrc + (size_t)c * (kGemmBBytes / 4), kGemmBBytes, &full[s]);
-                    if (++s == kGemmStages) { s = 0; ph ^= 1u; }
+                    mbar_wait(&raw_empty[s], ph ^ 1u);
+                    if (WB_GEMM_ELECT_PROD ? elect_one_sync() : (lane == 0)) {
+                        mbar_arrive_expect_tx(&raw_full[s], kGemmABytes);
+                        tma_load_2d(raw + (size_t)s * kGemmABytes, &tmap, c * kGemmBK, row0, &raw_full[s]);
+                    }
+                    __syncwarp();
+                    if (++s == kRaw) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // =============================== producer B: query images (ring 2) ==========================
+        {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int qb = (int)(w % p.nqb);
+                const float* bsrc = p.bimg + (size_t)qb * p.nchunks * (kBBytes / 4);
+                for (int c = 0; c < p.nchunks; ++c) {
+                    mbar_wait(&slot_empty[s], ph ^ 1u);
+                    if (WB_GEMM_ELECT_PROD ? elect_one_sync() : (lane == 0)) {
+                        mbar_arrive_expect_tx(&b_full[s], kBBytes);
+                        bulk_g2s(bimg_s + (size_t)s * kBBytes, bsrc + (size_t)c * (kBBytes / 4), kBBytes, &b_full[s]);
+                    }
+                    __syncwarp();
+                    if (++s == kSlots) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer =============================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(kGemmBM, kGemmBN);
+        {   // converged warp; the elected lane issues the MMAs and the commits that track them
+            constexpr uint32_t idesc = umma_idesc_tf32(kGemmBM, BN);
+            const uint64_t desc_hi0 = umma_smem_desc(smem_u32(bimg_s), BN * 16, 128);  // slot 0, k-step 0
             int s = 0;
             uint32_t ph = 0;
             int buf = 0;
@@ -242,41 +297,52 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
                 mbar_wait(&d_empty[buf], dph ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kGemmBN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
                 for (int c = 0; c < p.nchunks; ++c) {
-                    mbar_wait(&full[s], ph);    // B image landed
+                    mbar_wait(&b_full[s], ph);  // query image landed
                     mbar_wait(&a_full[s], ph);  // A hi/lo written to TMEM
                     tc_fence_after();
-                    const uint32_t b_hi = smem_u32(stages + (size_t)s * kGemmStageBytes + kGemmABytes);
-                    const uint32_t b_lo = b_hi + kGemmBBytes / 2;
-                    const uint32_t a_hi = tmem_base + (uint32_t)(kTmemAOff + s * 64);
-                    const uint32_t a_lo = a_hi + 32;
+                    if (WB_GEMM_ELECT_MMA ? elect_one_sync() : (lane == 0)) {
+                        const uint32_t a_hi = tmem_base + (uint32_t)(kTmemAOff + s * 64);
+                        const uint32_t a_lo = a_hi + 32;
+                        // descriptors differ only in the start-address field: add (bytes >> 4) to the low word
+                        const uint64_t dh0 = desc_hi0 + (uint64_t)(((uint32_t)s * kBBytes) >> 4);
+                        const uint64_t dl0 = dh0 + (uint64_t)((kBBytes / 2) >> 4);
 #pragma unroll
-                    for (int j = 0; j < kGemmBK / 8; ++j) {
-                        // one k-step = 8 tf32 = two 16-byte k columns: LBO = 2048 B, SBO = 128 B
-                        const uint64_t dh = umma_smem_desc(b_hi + j * 4096, 2048, 128);
-                        const uint64_t dl = umma_smem_desc(b_lo + j * 4096, 2048, 128);
-                        umma_tf32_ts(d_tmem, a_hi + j * 8, dh, idesc, (c | j) != 0);
-                        umma_tf32_ts(d_tmem, a_hi + j * 8, dl, idesc, 1);
-                        umma_tf32_ts(d_tmem, a_lo + j * 8, dh, idesc, 1);
+                        for (int j = 0; j < kGemmBK / 8; ++j) {
+                            // one k-step = 8 tf32 = two 16-byte k columns: LBO = BN*16 B, SBO = 128 B
+                            const uint64_t dh = dh0 + (uint64_t)((j * 2 * BN * 16) >> 4);
+                            const uint64_t dl = dl0 + (uint64_t)((j * 2 * BN * 16) >> 4);
+                            umma_tf32_ts(d_tmem, a_hi + j * 8, dh, idesc, (c | j) != 0);
+                            if (p.debug_terms > 1) umma_tf32_ts(d_tmem, a_hi + j * 8, dl, idesc, 1);
+                            if (p.debug_terms > 2) umma_tf32_ts(d_tmem, a_lo + j * 8, dh, idesc, 1);
+                        }
+                        umma_commit(&slot_empty[s]);  // slot (smem image + TMEM A) is free once these MMAs retire
+                        if (c == p.nchunks - 1) umma_commit(&d_full[buf]);
                     }
-                    umma_commit(&empty[s]);  // stage (smem B + TMEM A) is free once these MMAs retire
-                    if (++s == kGemmStages) { s = 0; ph ^= 1u; }
+                    __syncwarp();
+                    if (++s == kSlots) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(&d_full[buf]);
                 if (++buf == 2) { buf = 0; dph ^= 1u; }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if ((warp >= 4 && warp < 8) || warp >= 12) {
         // =============================== transform: fp32 -> (hi, lo) in TMEM ======================
+        // Two sets of four warps take alternate k-chunks, so the LDS -> split -> tcgen05.st -> wait::st
+        // latency chain of one chunk overlaps the next chunk's.
+        const int set = warp >= 12 ? 1 : 0;
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
-        int s = 0;
-        uint32_t ph = 0;
+        int64_t g = 0;                      // running chunk number over all work items of this CTA
         for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
-            for (int c = 0; c < p.nchunks; ++c) {
-                mbar_wait(&full[s], ph);
-                const unsigned char* a_raw = stages + (size_t)s * kGemmStageBytes + (size_t)r * 128;
+            for (int c = 0; c < p.nchunks; ++c, ++g) {
+                if ((g & 1) != set) continue;
+                const int sr = (int)(g % kRaw);
+                const uint32_t phr = (uint32_t)((g / kRaw) & 1);
+                const int ss = (int)(g % kSlots);
+                const uint32_t phs = (uint32_t)((g / kSlots) & 1);
+                mbar_wait(&raw_full[sr], phr);
+                const unsigned char* a_raw = raw + (size_t)sr * kGemmABytes + (size_t)r * 128;
                 uint32_t hi[32], lo[32];
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
@@ -289,20 +355,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                         lo[ch * 4 + e] = __float_as_uint(x[e] - __uint_as_float(h));
                     }
                 }
-                const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kTmemAOff + s * 64);
+                // NOTE: the raw stage is handed back only AFTER the TMEM store below.  Releasing it here
+                // ("the tile is in registers") was measured to race on B200: the next TMA load overwrote the
+                // top rows of the stage before they had been read (profiles/r01/gemm_experiments.md).
+                mbar_wait(&slot_empty[ss], phs ^ 1u);        // the MMAs that last read this TMEM slot have retired
+                tc_fence_after();
+                const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kTmemAOff + ss * 64);
                 tmem_st32(ta, hi);
                 tmem_st32(ta + 32, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(&a_full[s]);
-                    mbar_arrive(&empty[s]);  // raw tile consumed
+                    mbar_arrive(&a_full[ss]);
+                    mbar_arrive(&raw_empty[sr]);
                 }
-                if (++s == kGemmStages) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 12) {
         // =============================== epilogue: threshold filter ================================
         const int quarter = warp & 3;
         const int etid = tid - 8 * 32;
@@ -313,23 +383,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             const int qb = (int)(w - tile * p.nqb);
             const int64_t row = p.row_begin + tile * kGemmBM + quarter * 32 + lane;
             const bool row_ok = row < p.row_end;
-            thr_s[buf * kGemmBN + etid] = p.thr[qb * kGemmBN + etid];
+            if (etid < BN) thr_s[buf * BN + etid] = p.thr[qb * BN + etid];
             named_bar_sync(kBarEpilogue, 128);
             mbar_wait(&d_full[buf], dph);
             tc_fence_after();
-            const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kGemmBN);
+            const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
-            for (int cb = 0; cb < kGemmBN / 32; ++cb) {
+            for (int cb = 0; cb < BN / 32; ++cb) {
                 uint32_t v[32];
                 tmem_ld32(td + cb * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float sc = __uint_as_float(v[j]);
-                    const bool pass = row_ok && sc > thr_s[buf * kGemmBN + cb * 32 + j];
+                    const bool pass = row_ok && sc > thr_s[buf * BN + cb * 32 + j];
                     const unsigned m = __ballot_sync(0xffffffffu, pass);
                     if (m) {
-                        const int qi = qb * kGemmBN + cb * 32 + j;  // < nq: padded queries have thr = +inf
+                        const int qi = qb * BN + cb * 32 + j;  // < nq: padded queries have thr = +inf
                         int base = 0;
                         if (lane == (__ffs(m) - 1)) base = atomicAdd(&p.cnt[qi], __popc(m));
                         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
@@ -355,8 +425,5 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
 }
-
-constexpr size_t kGemmSmemBytes =
-    1024 + (size_t)kGemmStages * kGemmStageBytes + (3 * kGemmStages + 4) * 8 + 16 + 2 * kGemmBN * 4;
 
 }  // namespace wb
