@@ -299,7 +299,7 @@ def run_ours(a):
             t = json.load(open(tf))
             if t.get("rows") == hi - lo and t.get("dim") == a.dim and t.get("batch") == a.batch:
                 traffic = t.get("dram_bytes_per_launch")
-        if a.batch < 9:   # K1: CUDA-core scan, HBM-bound; one pass of the row store per <= 8 queries
+        if a.batch < 5:   # K1: CUDA-core scan, HBM-bound; one pass of the row store per <= 8 queries
             passes = (a.batch + 7) // 8
             achieved = local_bytes * passes / (scan_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
