@@ -92,6 +92,20 @@ int wb_search_dev(wb_index* h, int64_t nq, const float* q_dev, int64_t k, int64_
 int wb_merge_topk_dev(int device, int64_t nq, int64_t k, int64_t nparts, const float* D_parts_dev,
                       const int64_t* I_parts_dev, float* D_dev, int64_t* I_dev, void* stream);
 
+/* ---- multi-GPU exchange over NVLink peer memory (one process per GPU) ---------------------------
+ * The all-gather of the k candidates and the final merge as ONE kernel: every rank stores its rows
+ * straight into the mailboxes of its peers (cudaIpc-mapped), raises per-query flags, waits for the
+ * others' flags and merges.  Setup: wb_exch_create on every rank, exchange the 64-byte handles
+ * (any host-side all-gather), wb_exch_open_peers.  Every rank must then call
+ * wb_exch_merge_dev the same number of times with the same nq and k. */
+typedef struct wb_exchange wb_exchange;
+int wb_exch_create(int device, int rank, int world, int64_t max_queries, int64_t max_entries, wb_exchange** out);
+int wb_exch_local_handle(wb_exchange* ex, void* handle64 /* 64 bytes out */);
+int wb_exch_open_peers(wb_exchange* ex, const void* handles /* [world][64] */);
+int wb_exch_merge_dev(wb_exchange* ex, int64_t nq, int64_t k, const float* D_local_dev, const int64_t* I_local_dev,
+                      float* D_dev, int64_t* I_dev, void* stream);
+int wb_exch_free(wb_exchange* ex);
+
 /* ---- row access ------------------------------------------------------------------------- */
 /* index.reconstruct_batch(ids)   api/routes.py:1078 (after index.make_direct_map, :907).
  * Looks rows up by external id; an unknown id is an error (faiss raises). */

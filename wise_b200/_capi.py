@@ -43,6 +43,11 @@ SIGNATURES = {
     "wb_search": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, _vp]),
     "wb_search_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp]),
     "wb_merge_topk_dev": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "wb_exch_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(_vp)]),
+    "wb_exch_local_handle": (C.c_int, [_vp, _vp]),
+    "wb_exch_open_peers": (C.c_int, [_vp, _vp]),
+    "wb_exch_merge_dev": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "wb_exch_free": (C.c_int, [_vp]),
     "wb_reconstruct_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
     "wb_export_rows": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp]),
     "wb_ivf_add_preassigned": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/wise_b200.h"
+#include "exchange.cuh"
 #include "gemm.cuh"
 #include "kmeans.cuh"
 #include "merge.cuh"
@@ -1101,5 +1102,112 @@ extern "C" int wb_ivf_train(wb_index* h, int64_t n, const float* x_host, int nit
     }
     if (e != cudaSuccess) return fail("k-means training failed: %s", cudaGetErrorString(e));
     h->trained = true;
+    return 0;
+}
+
+// ---- multi-GPU exchange over peer memory ----------------------------------------------------------
+struct wb_exchange {
+    int device = 0, rank = 0, world = 1;
+    size_t region_bytes = 0, flags_bytes = 0, cap_entries = 0, nq_cap = 0, total_bytes = 0;
+    unsigned char* local = nullptr;
+    unsigned char* peers[kExchMaxWorld] = {};
+    bool opened[kExchMaxWorld] = {};
+    uint32_t seq = 0;
+};
+
+extern "C" int wb_exch_create(int device, int rank, int world, int64_t max_queries, int64_t max_entries,
+                              wb_exchange** out) {
+    if (!out) return fail("out is NULL");
+    *out = nullptr;
+    if (world < 1 || world > kExchMaxWorld || rank < 0 || rank >= world) return fail("bad rank/world %d/%d", rank, world);
+    if (max_queries < 1 || max_entries < max_queries) return fail("bad exchange capacity");
+    CK(cudaSetDevice(device));
+    wb_exchange* ex = new wb_exchange();
+    ex->device = device;
+    ex->rank = rank;
+    ex->world = world;
+    ex->nq_cap = (size_t)max_queries;
+    ex->cap_entries = ((size_t)max_entries + 3) & ~(size_t)3;
+    ex->flags_bytes = ((size_t)max_queries * 4 + 255) & ~(size_t)255;
+    ex->region_bytes = (ex->flags_bytes + ex->cap_entries * 12 + 255) & ~(size_t)255;
+    ex->total_bytes = ex->region_bytes * 2 * world;
+    CK(cudaMalloc(&ex->local, ex->total_bytes));
+    CK(cudaMemset(ex->local, 0, ex->total_bytes));
+    CK(cudaDeviceSynchronize());
+    ex->peers[rank] = ex->local;
+    *out = ex;
+    return 0;
+}
+
+extern "C" int wb_exch_local_handle(wb_exchange* ex, void* handle64) {
+    if (!ex || !handle64) return fail("NULL argument");
+    CK(cudaSetDevice(ex->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hnd;
+    CK(cudaIpcGetMemHandle(&hnd, ex->local));
+    memcpy(handle64, &hnd, 64);
+    return 0;
+}
+
+extern "C" int wb_exch_open_peers(wb_exchange* ex, const void* handles /* [world][64] */) {
+    if (!ex || !handles) return fail("NULL argument");
+    CK(cudaSetDevice(ex->device));
+    for (int r = 0; r < ex->world; ++r) {
+        if (r == ex->rank) continue;
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, (const char*)handles + (size_t)r * 64, 64);
+        void* ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+        ex->peers[r] = (unsigned char*)ptr;
+        ex->opened[r] = true;
+    }
+    return 0;
+}
+
+extern "C" int wb_exch_free(wb_exchange* ex) {
+    if (!ex) return 0;
+    cudaSetDevice(ex->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < ex->world; ++r)
+        if (ex->opened[r]) cudaIpcCloseMemHandle(ex->peers[r]);
+    cudaFree(ex->local);
+    delete ex;
+    return 0;
+}
+
+// Global top-k from this rank's local (D, I): one kernel does the NVLink exchange and the merge.
+// Every rank must call this the same number of times with the same nq and k.
+extern "C" int wb_exch_merge_dev(wb_exchange* ex, int64_t nq, int64_t k, const float* D_local_dev,
+                                 const int64_t* I_local_dev, float* D_dev, int64_t* I_dev, void* stream) {
+    if (!ex) return fail("NULL exchange");
+    if (k < 1 || k > WB_MAX_K) return fail("k=%lld out of range [1, %d]", (long long)k, WB_MAX_K);
+    if (nq < 1 || (size_t)nq > ex->nq_cap || (size_t)(nq * k) > ex->cap_entries)
+        return fail("exchange capacity exceeded (nq=%lld, k=%lld)", (long long)nq, (long long)k);
+    for (int r = 0; r < ex->world; ++r)
+        if (!ex->peers[r]) return fail("peer %d is not mapped: call wb_exch_open_peers first", r);
+    CK(cudaSetDevice(ex->device));
+    ExchParams p{};
+    p.rank = ex->rank;
+    p.world = ex->world;
+    p.nq = nq;
+    p.k = (int)k;
+    p.S = merge_buffer_entries((int)k, ex->world);
+    p.seq = ++ex->seq;
+    if (p.seq == 0) p.seq = ++ex->seq;
+    p.D_local = D_local_dev;
+    p.I_local = I_local_dev;
+    for (int r = 0; r < ex->world; ++r) p.mailbox[r] = ex->peers[r];
+    p.region_bytes = ex->region_bytes;
+    p.flags_bytes = ex->flags_bytes;
+    p.cap_entries = ex->cap_entries;
+    p.D = D_dev;
+    p.I = I_dev;
+    static thread_local bool attr_done[64] = {};
+    if (ex->device >= 64 || !attr_done[ex->device]) {
+        CK(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        if (ex->device < 64) attr_done[ex->device] = true;
+    }
+    exchange_merge_kernel<<<(unsigned)nq, kMergeThreads, (size_t)p.S * 8, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
     return 0;
 }

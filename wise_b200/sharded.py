@@ -15,6 +15,7 @@ set of a query is the union over ranks, so the same merge applies.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable
 
 import numpy as np
@@ -49,6 +50,49 @@ def _cuda_merge(Dp: torch.Tensor, Ip: torch.Tensor):
     return D, I
 
 
+class PeerExchange:
+    """wb_exchange: the all-gather + merge as one kernel over NVLink peer memory (exchange.cuh).
+    Mailbox handles travel once through torch.distributed; after that no NCCL call is on the search path."""
+
+    def __init__(self, group=None, max_queries: int = 4096, max_entries: int = 1 << 20):
+        import ctypes as C
+        from . import _capi
+        self._capi, self._C = _capi, C
+        L = _capi.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.cuda.current_device()
+        self.h = C.c_void_p()
+        _capi.check(L.wb_exch_create(self.device, self.rank, self.world, max_queries, max_entries, C.byref(self.h)))
+        mine = C.create_string_buffer(64)
+        _capi.check(L.wb_exch_local_handle(self.h, mine))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine.raw), group=group)
+        blob = C.create_string_buffer(b"".join(handles), 64 * self.world)
+        _capi.check(L.wb_exch_open_peers(self.h, blob))
+        dist.barrier(group=group)
+        self.max_queries, self.max_entries = max_queries, max_entries
+
+    def fits(self, nq: int, k: int) -> bool:
+        return nq <= self.max_queries and nq * k <= self.max_entries
+
+    def merge(self, D: torch.Tensor, I: torch.Tensor):
+        nq, k = D.shape
+        Do = torch.empty_like(D)
+        Io = torch.empty_like(I)
+        st = torch.cuda.current_stream(D.device).cuda_stream
+        self._capi.check(self._capi.lib().wb_exch_merge_dev(self.h, nq, k, D.data_ptr(), I.data_ptr(), Do.data_ptr(),
+                                                            Io.data_ptr(), st))
+        return Do, Io
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                self._capi.lib().wb_exch_free(h)
+            except Exception:
+                pass
+
+
 class ShardedIndex:
     """A faiss-like index whose rows live on `world_size` GPUs (this process owns one shard).
 
@@ -65,6 +109,13 @@ class ShardedIndex:
         self._local_search = local_search or _cuda_local_search
         self._merge = merge or _cuda_merge
         self.d = local_index.d
+        # exchange step: "peer" = one fused kernel over NVLink peer memory (default on GPUs),
+        # "nccl" = all-gather + merge kernel.  CPU/gloo tests always take the all-gather path.
+        self.exchange = None
+        mode = os.environ.get("WISE_B200_EXCHANGE", "peer")
+        if (self.world > 1 and mode == "peer" and local_search is None and merge is None
+                and dist.get_backend(group) == "nccl"):
+            self.exchange = PeerExchange(group)
 
     @property
     def ntotal(self) -> int:
@@ -88,6 +139,8 @@ class ShardedIndex:
         if self.world == 1:
             return D, I
         nq, kk = D.shape
+        if self.exchange is not None and self.exchange.fits(nq, kk):
+            return self.exchange.merge(D.contiguous(), I.contiguous())
         Dp = torch.empty((self.world * nq, kk), dtype=D.dtype, device=D.device)
         Ip = torch.empty((self.world * nq, kk), dtype=I.dtype, device=I.device)
         dist.all_gather_into_tensor(Dp, D.contiguous(), group=self.group)  # concatenated along dim 0
