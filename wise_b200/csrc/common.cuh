@@ -127,14 +127,15 @@ __host__ __device__ __forceinline__ int pow2_ceil(int v) {
 template <int NT>
 __device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int P, int nlists, int tid, int bar_id) {
     const int half = P >> 1;
-    const int total = nlists * half;
+    const int lg_half = 31 - __clz(half);  // P is a power of two: no integer division in the loops
+    const int total = nlists << lg_half;
     for (int size = 2; size <= P; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int i = tid; i < total; i += NT) {
-                const int l = i / half;
-                const int j = i - l * half;
+                const int l = i >> lg_half;
+                const int j = i & (half - 1);
                 const int pos = 2 * j - (j & (stride - 1));
-                uint64_t* base = keys + (size_t)l * P;
+                uint64_t* base = keys + ((size_t)l << (lg_half + 1));
                 const uint64_t a = base[pos], b = base[pos + stride];
                 const bool desc = ((pos & size) == 0);
                 if ((a < b) == desc) {

@@ -84,7 +84,10 @@ __global__ void __launch_bounds__(kMergeThreads) exchange_merge_kernel(const Exc
         const volatile float* vD = sD;
         return vI[q * k + slot] >= 0 ? make_key(vD[q * k + slot], (uint32_t)c) : 0ull;
     };
-    block_select_topk(buf, p.S, k, M, load, &cnt);
+    if (!block_select_topk_lists(buf, p.S, k, p.world, [&](int l, int r) { return load((int64_t)l * k + r); }, &cnt)) {
+        __syncthreads();
+        block_select_topk(buf, p.S, k, M, load, &cnt);
+    }
     const unsigned char* myreg0 = exch_region(p, p.rank, b, 0);
     for (int j = tid; j < k; j += kMergeThreads) {
         const uint64_t key = buf[j];

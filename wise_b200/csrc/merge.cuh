@@ -79,6 +79,49 @@ __device__ __forceinline__ void block_select_topk(uint64_t* buf, int S, int k, i
     __syncthreads();
 }
 
+// Top-k of `nlists` SORTED (descending) lists of k keys each, load(list, rank) -> key.  Round 0 sorts only
+// the best j = S / nlists entries of every list; the k-th best of those is already (almost always) the final
+// threshold, and because the lists are sorted one compare per list decides whether anything deeper can
+// matter.  Lists that do reach deeper push their surviving tail; if that ever overflows the queue the
+// caller falls back to the generic block_select_topk.  Returns false on overflow (uniform).
+template <class Load2>
+__device__ __forceinline__ bool block_select_topk_lists(uint64_t* buf, int S, int k, int nlists, Load2 load, int* cnt) {
+    const int tid = threadIdx.x;
+    const int j0 = min(k, max(1, S / max(nlists, 1)));
+    const int n0 = nlists * j0;
+    if (n0 > S) return false;  // more lists than buffer entries (uniform)
+    for (int i = tid; i < S; i += kMergeThreads) buf[i] = i < n0 ? load(i / j0, i % j0) : 0ull;
+    if (tid == 0) *cnt = 0;
+    __syncthreads();
+    int Ps = 2;
+    while (Ps < n0) Ps <<= 1;  // sort only as much as is filled
+    Ps = max(Ps, 2);
+    bitonic_sort_desc<kMergeThreads>(buf, min(Ps, S), 1, tid, -1);
+    if (j0 >= k) return true;
+    const int qcap = S - k;
+    for (int i = k + tid; i < S; i += kMergeThreads) buf[i] = 0ull;
+    __syncthreads();
+    const uint64_t thr = buf[k - 1];
+    for (int l = tid; l < nlists; l += kMergeThreads) {
+        for (int r = j0; r < k; ++r) {
+            const uint64_t key = load(l, r);
+            if (!(key > thr)) break;  // sorted list: nothing below can pass either
+            const int slot = atomicAdd(cnt, 1);
+            if (slot < qcap) buf[k + slot] = key;
+        }
+    }
+    __syncthreads();
+    const int c = *cnt;
+    if (c > qcap) return false;
+    if (c > 0) {
+        int P2 = 2;
+        while (P2 < k + c) P2 <<= 1;
+        bitonic_sort_desc<kMergeThreads>(buf, min(P2, S), 1, tid, -1);
+    }
+    __syncthreads();
+    return true;
+}
+
 template <bool FROM_KEYS>
 __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergeParams p) {
     extern __shared__ __align__(16) unsigned char smem_merge[];
@@ -88,7 +131,13 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergePa
     const int64_t q = blockIdx.x;
     const int k = p.k;
     const int64_t M = p.nparts * (int64_t)k;
-    block_select_topk(buf, p.S, k, M, [&](int64_t c) { return merge_load<FROM_KEYS>(p, q, M, c); }, &cnt);
+    // both sources are nparts sorted lists of k keys
+    const bool ok = block_select_topk_lists(
+        buf, p.S, k, (int)p.nparts, [&](int l, int r) { return merge_load<FROM_KEYS>(p, q, M, (int64_t)l * k + r); }, &cnt);
+    if (!ok) {
+        __syncthreads();
+        block_select_topk(buf, p.S, k, M, [&](int64_t c) { return merge_load<FROM_KEYS>(p, q, M, c); }, &cnt);
+    }
     for (int j = tid; j < k; j += kMergeThreads) {
         const uint64_t key = buf[j];
         float d = -FLT_MAX;
