@@ -67,6 +67,8 @@ int wb_ivf_train(wb_index* h, int64_t n, const float* x_host, int niter, int64_t
  * index (read_index) and to compare search on the reference's own centroids. */
 int wb_ivf_set_centroids(wb_index* h, const float* centroids_host /* [nlist*d] */);
 int wb_ivf_get_centroids(const wb_index* h, float* centroids_host /* [nlist*d] */);
+/* A trainer that drives the k-means pieces below itself (sharded training) declares the result final. */
+int wb_ivf_mark_trained(wb_index* h);
 /* One k-means iteration from the current centroids over device-resident points; exposed so a
  * sharded trainer can all-reduce sums/counts between the two halves.
  *   assign: x -> int32 list per row, objective = sum of max inner products

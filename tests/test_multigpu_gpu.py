@@ -61,3 +61,50 @@ def test_two_gpu_sharded_equals_single(tmp_path, mode):
         assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
         O.compare_topk(D0, I0, Dr, Ir, band=4e-6)
         assert I0[-1, 0] == ids[3] and I0[-1, 1] == ids[n - 50 + 3]  # exact tie across ranks: lowest position first
+
+
+def _train_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WISE_B200_DEVICE=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from wise_b200 import faiss_compat as faiss
+        from wise_b200.sharded import ShardedIndex, shard_range, train_ivf_sharded
+        n, d, k = 40000, 64, 100
+        x = O.clustered_unit(n, d, 100, 31)
+        lo, hi = shard_range(n, rank, world)
+        ivf = faiss.IndexIVFFlat(faiss.IndexFlatIP(d, device=rank), d, k, faiss.METRIC_INNER_PRODUCT)
+        objs = train_ivf_sharded(ivf, torch.from_numpy(x[lo:hi]).cuda(rank))
+        assert ivf.is_trained and ivf.quantizer.ntotal == k
+        cent = ivf.centroids()
+        ivf.add_with_ids(x[lo:hi], np.arange(lo, hi, dtype=np.int64))
+        ivf.nprobe = 8
+        sh = ShardedIndex(ivf)
+        D, I = sh.search(x[:6], 10)
+        np.savez(os.path.join(out, f"train_r{rank}.npz"), cent=cent, objs=np.asarray(objs), D=D, I=I)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_kmeans_and_ivf_search(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_train_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (np.load(tmp_path / f"train_r{r}.npz") for r in (0, 1))
+    assert np.array_equal(r0["cent"], r1["cent"])  # replicated centroids stay bit-identical
+    objs = r0["objs"]
+    assert objs[-1] > objs[0] and np.allclose(np.linalg.norm(r0["cent"], axis=1), 1.0, atol=1e-4)
+    n, d, k = 40000, 64, 100
+    x = O.clustered_unit(n, d, 100, 31)
+    c_ref, objs_ref = O.kmeans_train(x, k)
+    obj_gpu = float(np.max(x.astype(np.float64) @ r0["cent"].astype(np.float64).T, axis=1).sum())
+    obj_ref = float(np.max(x.astype(np.float64) @ c_ref.astype(np.float64).T, axis=1).sum())
+    assert obj_gpu >= 0.99 * obj_ref, (obj_gpu, obj_ref)
+    # sharded IVF search == single logical IVF index with the same centroids (oracle), on both ranks
+    a = O.ivf_assign(x, r0["cent"])
+    Dr, Ir = O.ivf_search(x, None, a, r0["cent"], x[:6], 10, 8)
+    assert np.array_equal(r0["I"], r1["I"])
+    O.compare_topk(r0["D"], r0["I"], Dr, Ir, band=4e-6)

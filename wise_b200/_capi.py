@@ -37,6 +37,7 @@ SIGNATURES = {
     "wb_ivf_train": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, C.c_int64]),
     "wb_ivf_set_centroids": (C.c_int, [_vp, _vp]),
     "wb_ivf_get_centroids": (C.c_int, [_vp, _vp]),
+    "wb_ivf_mark_trained": (C.c_int, [_vp]),
     "wb_kmeans_assign_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.POINTER(C.c_double), _vp]),
     "wb_kmeans_accumulate_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "wb_kmeans_update_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), _vp]),

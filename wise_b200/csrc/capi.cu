@@ -917,6 +917,12 @@ extern "C" int wb_ivf_set_centroids(wb_index* h, const float* c) {
     return 0;
 }
 
+extern "C" int wb_ivf_mark_trained(wb_index* h) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    h->trained = true;
+    return 0;
+}
+
 extern "C" int wb_ivf_get_centroids(const wb_index* h, float* c) {
     if (!h || !h->ivf) return fail("not an IVF index");
     if (!c) return fail("NULL centroids");

@@ -154,3 +154,65 @@ class ShardedIndex:
         nprobe = getattr(self.local, "nprobe", 1)
         D, I = self.search_dev(q, int(k), int(nprobe))
         return D.cpu().numpy(), I.cpu().numpy()
+
+
+def train_ivf_sharded(index, x_local: torch.Tensor, niter: int = 10, seed: int = 1234, group=None, verbose: bool = False):
+    """index.train() with the training rows sharded over the ranks: every rank assigns and
+    accumulates ITS rows (K6/K7 on its GPU), one all-reduce of [nlist*d sums | nlist counts] per iteration,
+    then every rank applies the identical centroid update, so the centroids stay replicated bit for bit.
+    Mirrors faiss Clustering::train for IndexIVFFlat(METRIC_INNER_PRODUCT): spherical, niter=10, seed=1234,
+    initial centroids = k random training rows.  `index` is this rank's (empty, untrained) IndexIVFFlat;
+    x_local is a float32 [n_local, d] CUDA tensor.  Returns the objective (sum of max inner products) per iteration."""
+    import ctypes as C
+    from . import _capi
+    L = _capi.lib()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    dev = x_local.device
+    x_local = x_local.contiguous()
+    n_local, d = x_local.shape
+    k = index.nlist
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    counts[rank] = n_local
+    if world > 1:
+        dist.all_reduce(counts, group=group)
+    n_total = int(counts.sum().item())
+    if n_total < k:
+        raise RuntimeError(f"Number of training points ({n_total}) should be at least as large as number of clusters ({k})")
+    # initial centroids: k distinct global rows from a seeded permutation (same on every rank)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed + 1)
+    pick = torch.randperm(n_total, generator=g)[:k]
+    lo = int(counts[:rank].sum().item())
+    mine = (pick >= lo) & (pick < lo + n_local)
+    init = torch.zeros((k, d), dtype=torch.float32, device=dev)
+    init[mine.nonzero().squeeze(1).to(dev)] = x_local[(pick[mine] - lo).to(dev)]
+    if world > 1:
+        dist.all_reduce(init, group=group)
+    init = torch.nn.functional.normalize(init, dim=1)
+    _capi.check(L.wb_ivf_set_centroids(index._h, _capi.ptr(np.ascontiguousarray(init.cpu().numpy()))))
+    st = torch.cuda.current_stream(dev).cuda_stream
+    assign = torch.empty(n_local, dtype=torch.int32, device=dev)
+    sums = torch.empty((k, d), dtype=torch.float32, device=dev)
+    cnts = torch.empty(k, dtype=torch.int64, device=dev)
+    objs = []
+    for it in range(niter):
+        obj = C.c_double(0)
+        _capi.check(L.wb_kmeans_assign_dev(index._h, n_local, x_local.data_ptr(), assign.data_ptr(), C.byref(obj), st))
+        _capi.check(L.wb_kmeans_accumulate_dev(index._h, n_local, x_local.data_ptr(), assign.data_ptr(), sums.data_ptr(),
+                                               cnts.data_ptr(), st))
+        o = torch.tensor([obj.value], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(sums, group=group)
+            dist.all_reduce(cnts, group=group)
+            dist.all_reduce(o, group=group)
+        torch.cuda.synchronize(dev)
+        nsplit = C.c_int64(0)
+        _capi.check(L.wb_kmeans_update_dev(index._h, sums.data_ptr(), cnts.data_ptr(), n_total, 1234, C.byref(nsplit), st))
+        torch.cuda.synchronize(dev)
+        objs.append(float(o.item()))
+        if verbose and rank == 0:
+            print(f"  k-means iteration {it}: objective {objs[-1]:.4f}, split {nsplit.value}", flush=True)
+    _capi.check(L.wb_ivf_mark_trained(index._h))
+    index._sync_quantizer()
+    return objs
