@@ -280,8 +280,8 @@ def _read_ivf(f):
             f.seek(codes_at + s * d * 4)
             x = np.frombuffer(_need(f, mm * d * 4), np.float32).reshape(mm, d)
             a = np.full(mm, l, np.int32)
-            _capi.check(_capi.lib().wb_ivf_add_preassigned(index._h, mm, _capi.ptr(x), _capi.ptr(np.ascontiguousarray(ids[s:s + mm])),
-                                                           _capi.ptr(a)))
+            ids_c = np.ascontiguousarray(ids[s:s + mm])  # keep a reference: the C call borrows this buffer
+            _capi.check(_capi.lib().wb_ivf_add_preassigned(index._h, mm, _capi.ptr(x), _capi.ptr(ids_c), _capi.ptr(a)))
         f.seek(end)
     if dm_type == fc.DirectMap.Array:
         index.direct_map.type = fc.DirectMap.Array

@@ -190,7 +190,8 @@ def train_ivf_sharded(index, x_local: torch.Tensor, niter: int = 10, seed: int =
     if world > 1:
         dist.all_reduce(init, group=group)
     init = torch.nn.functional.normalize(init, dim=1)
-    _capi.check(L.wb_ivf_set_centroids(index._h, _capi.ptr(np.ascontiguousarray(init.cpu().numpy()))))
+    init_h = np.ascontiguousarray(init.cpu().numpy())  # keep a reference: the C call borrows this buffer
+    _capi.check(L.wb_ivf_set_centroids(index._h, _capi.ptr(init_h)))
     st = torch.cuda.current_stream(dev).cuda_stream
     assign = torch.empty(n_local, dtype=torch.int32, device=dev)
     sums = torch.empty((k, d), dtype=torch.float32, device=dev)
