@@ -50,11 +50,14 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--sweep", default="", help="comma list of extra batch sizes to report, e.g. 2,4,8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mixed", action="store_true",
+                    help="config 5: half of the batch are 'combined' queries normalise(2.0*t + 1.0*i - 0.2*n) "
+                         "(/root/reference/api/routes.py:759-850)")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return f"IndexFlatIP top-{a.k} over {a.rows}x{a.dim} fp32, query batch {a.batch}"
+    return f"IndexFlatIP top-{a.k} over {a.rows}x{a.dim} fp32, query batch {a.batch}" + (" (mixed text/combined)" if a.mixed else "")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -85,13 +88,24 @@ def fill_index_clustered(index, lo, hi, d, seed, device, chunk=500_000, ncentres
     return centres, sample
 
 
+MIXED = False
+
+
 def make_queries(centres, nq, d, seed, device):
     import torch
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
-    j = torch.randint(0, centres.shape[0], (nq,), device=device, generator=gen)
-    q = centres[j] + 0.6 * torch.randn(nq, d, device=device, generator=gen) / (d ** 0.5)
-    return torch.nn.functional.normalize(q, dim=1).contiguous()
+
+    def draw(m):
+        j = torch.randint(0, centres.shape[0], (m,), device=device, generator=gen)
+        v = centres[j] + 0.6 * torch.randn(m, d, device=device, generator=gen) / (d ** 0.5)
+        return torch.nn.functional.normalize(v, dim=1)
+
+    q = draw(nq)
+    if MIXED and nq > 1:  # second half: text x2.0 + image x1.0 - negative x0.2, renormalised
+        h = nq // 2
+        q[h:] = torch.nn.functional.normalize(2.0 * q[h:] + 1.0 * draw(nq - h) - 0.2 * draw(nq - h), dim=1)
+    return q.contiguous()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -352,7 +366,9 @@ def run_ours(a):
 
 
 def main():
+    global MIXED
     a = parse()
+    MIXED = a.mixed
     # Keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner) get stderr.
     real_stdout = os.fdopen(os.dup(1), "w")
     sys.stdout.flush()
