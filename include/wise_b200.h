@@ -120,6 +120,15 @@ int wb_export_rows(wb_index* h, int64_t start, int64_t n, float* x_host, int64_t
 int wb_ivf_add_preassigned(wb_index* h, int64_t n, const float* x_host, const int64_t* ids_host,
                            const int32_t* assign_host);
 
+/* ---- FeatureStore fast ingest (host only, no GPU needed) -----------------------------------------------
+ * One pass over a WebdatasetStore shard `<media>-%06d.tar` (src/feature/store/webdataset_store.py:33-35):
+ * tar headers are walked directly and the float32 payload of every `%010d.features.pyd` member
+ * (pickle.dumps(ndarray (m,d) f32), :93-99) is located without creating python objects - replaces the
+ * per-vector loop of iter_batch (:116-141) that feeds index.add_with_ids (feature_search_index.py:79-82).
+ * A non-zero return means "use the python reader for this shard" (unknown pickle dialect, I/O error). */
+int wb_tar_scan(const char* path, int64_t* rows_out, int64_t* members_out, int64_t* d_out);
+int wb_tar_read(const char* path, int64_t d, int64_t cap, int64_t* ids_host, float* x_host, int64_t* rows_out);
+
 /* ---- introspection for bench.py / tests --------------------------------------------------- */
 /* Device pointer and row stride (floats) of the resident row store. */
 int wb_storage(wb_index* h, void** rows_dev, int64_t* ld);

@@ -111,3 +111,94 @@ def test_unpickler_rejects_non_numpy():
 def test_factory_rejects_mixed_or_missing(tmp_path):
     with pytest.raises(ValueError):
         FeatureStoreFactory.load_store("video", tmp_path)
+
+
+# ---- C++ shard reader (wb_tar_scan / wb_tar_read): host code, runs without a GPU ---------------------
+def _write_store(tmp_path, n, d, maxcount, protocol=None, dtype=np.float32):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((n, d)).astype(dtype)
+    w = WebdatasetStore("video", tmp_path)
+    w.enable_write(maxcount, 1 << 30)
+    for i in range(n):
+        w.add(3 * i + 1, x[i:i + 1])
+    w.close()
+    return x
+
+
+def test_fast_reader_matches_python_reader(tmp_path, monkeypatch):
+    x = _write_store(tmp_path, 2500, 48, 1000)
+    fast = WebdatasetStore("video", tmp_path)
+    fast.enable_read()
+    assert fast._shard_rows and sum(fast._shard_rows.values()) == 2500
+    fi, fx = zip(*fast.iter_batch())
+    monkeypatch.setenv("WISE_B200_FAST_STORE", "0")
+    slow = WebdatasetStore("video", tmp_path)
+    slow.enable_read()
+    assert not slow._shard_rows and (slow.feature_count, slow.feature_dim) == (fast.feature_count, fast.feature_dim) == (2500, 48)
+    si, sx = zip(*slow.iter_batch())
+    assert [len(b) for b in fi] == [len(b) for b in si] == [512, 512, 512, 512, 452]
+    assert np.array_equal(np.concatenate(fi), np.concatenate(si)) and np.array_equal(np.concatenate(fx), np.concatenate(sx))
+    assert np.array_equal(np.concatenate(fx), x) and np.array_equal(np.concatenate(fi), 3 * np.arange(2500) + 1)
+
+
+def test_fast_reader_c_abi_directly(tmp_path):
+    import ctypes as C
+    from wise_b200 import _capi
+    x = _write_store(tmp_path, 300, 16, 1000)
+    L = _capi.lib()
+    fn = str(tmp_path / "video-000000.tar").encode()
+    rows, members, d = C.c_int64(), C.c_int64(), C.c_int64()
+    assert L.wb_tar_scan(fn, C.byref(rows), C.byref(members), C.byref(d)) == 0
+    assert (rows.value, members.value, d.value) == (300, 300, 16)
+    ids = np.empty(300, np.int64); out = np.empty((300, 16), np.float32); n = C.c_int64()
+    assert L.wb_tar_read(fn, 16, 300, _capi.ptr(ids), _capi.ptr(out), C.byref(n)) == 0
+    assert n.value == 300 and np.array_equal(out, x) and ids[7] == 22
+    assert L.wb_tar_read(fn, 16, 10, _capi.ptr(ids), _capi.ptr(out), C.byref(n)) != 0  # buffer too small
+    assert L.wb_tar_scan(str(tmp_path / "nope.tar").encode(), C.byref(rows), C.byref(members), C.byref(d)) != 0
+
+
+def test_fast_reader_falls_back_on_foreign_samples(tmp_path):
+    """float64 arrays (the reference's own unit test writes int arrays) are not the fp32 fast path: python reads them."""
+    w = WebdatasetStore("test-store", tmp_path)
+    w.enable_write(3, 256)
+    f0 = np.concatenate((A, B, Cc), axis=0)
+    for i, f in ((0, f0), (3, f0[::-1].copy()), (6, A)):
+        w.add(i, f)
+    w.close()
+    r = WebdatasetStore("test-store", tmp_path)
+    r.enable_read()
+    assert [int(i) for i, _ in r] == [0, 3, 6] and r.feature_dim == 4 and r.feature_count == 3
+
+
+@pytest.mark.parametrize("protocol", [2, 3, 4, 5])
+def test_fast_reader_pickle_protocols(tmp_path, protocol):
+    """The scanner understands the ndarray pickles of every protocol a WISE install may have written."""
+    import ctypes as C
+    import io
+    from wise_b200 import _capi
+    rng = np.random.default_rng(protocol)
+    x = rng.standard_normal((5, 1, 33)).astype(np.float32)
+    fn = tmp_path / "video-000000.tar"
+    with tarfile.open(fn, "w") as tf:
+        for i in range(5):
+            data = pickle.dumps(x[i], protocol=protocol)
+            ti = tarfile.TarInfo("%010d.features.pyd" % (i + 10))
+            ti.size = len(data)
+            tf.addfile(ti, io.BytesIO(data))
+    L = _capi.lib()
+    rows, members, d = C.c_int64(), C.c_int64(), C.c_int64()
+    rc = L.wb_tar_scan(str(fn).encode(), C.byref(rows), C.byref(members), C.byref(d))
+    if protocol == 2:
+        # protocol 2 stores the payload as a latin-1 *text* string (UTF-8 in the file): not raw bytes, so the
+        # C++ reader must decline and the python reader takes the shard
+        assert rc != 0
+        r = WebdatasetStore("video", tmp_path)
+        r.enable_read()
+        got = np.concatenate([v for _, v in r.iter_batch()])
+        assert not r._shard_rows and np.array_equal(got, x[:, 0, :])
+        return
+    assert rc == 0, L.wb_last_error()
+    assert (rows.value, d.value) == (5, 33)
+    ids = np.empty(5, np.int64); out = np.empty((5, 33), np.float32); n = C.c_int64()
+    assert L.wb_tar_read(str(fn).encode(), 33, 5, _capi.ptr(ids), _capi.ptr(out), C.byref(n)) == 0
+    assert np.array_equal(out, x[:, 0, :]) and ids.tolist() == [10, 11, 12, 13, 14]

@@ -19,6 +19,7 @@
 #include "kmeans.cuh"
 #include "merge.cuh"
 #include "scan.cuh"
+#include "tarstore.h"
 
 using namespace wb;
 
@@ -1215,5 +1216,44 @@ extern "C" int wb_exch_merge_dev(wb_exchange* ex, int64_t nq, int64_t k, const f
     }
     exchange_merge_kernel<<<(unsigned)nq, kMergeThreads, (size_t)p.S * 8, (cudaStream_t)stream>>>(p);
     CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- FeatureStore fast ingest (host only) ------------------------------------------------------------
+// Count the feature rows of one WebdatasetStore shard and report their dimension.
+extern "C" int wb_tar_scan(const char* path, int64_t* rows_out, int64_t* members_out, int64_t* d_out) {
+    if (!path) return fail("NULL path");
+    int64_t rows = 0, members = 0, d = -1;
+    std::string why;
+    const int rc = wbtar::walk(path, [&](const wbtar::Sample& s) {
+        if (d < 0) d = s.d;
+        if (s.d != d) return 2;
+        rows += s.m;
+        members++;
+        return 0;
+    }, &why);
+    if (rc) return fail("wb_tar_scan(%s): %s (code %d)", path, why.empty() ? "mixed dimensions" : why.c_str(), rc), rc + 1;
+    if (rows_out) *rows_out = rows;
+    if (members_out) *members_out = members;
+    if (d_out) *d_out = d;
+    return 0;
+}
+
+// Decode one shard into caller-owned host buffers: ids[cap] (the sample key, repeated for multi-row samples),
+// x[cap*d] float32.  *rows_out = rows written.  Fails (non-zero) if the shard needs the python reader.
+extern "C" int wb_tar_read(const char* path, int64_t d, int64_t cap, int64_t* ids, float* x, int64_t* rows_out) {
+    if (!path || !ids || !x || !rows_out) return fail("NULL argument");
+    int64_t n = 0;
+    std::string why;
+    const int rc = wbtar::walk(path, [&](const wbtar::Sample& s) {
+        if (s.d != d) { why = "dimension changes inside the shard"; return 2; }
+        if (n + s.m > cap) { why = "buffer too small"; return 1; }
+        memcpy(x + (size_t)n * d, s.data, (size_t)s.m * d * 4);
+        for (int64_t r = 0; r < s.m; ++r) ids[n + r] = s.id;
+        n += s.m;
+        return 0;
+    }, &why);
+    if (rc) return fail("wb_tar_read(%s): %s (code %d)", path, why.c_str(), rc), rc + 1;
+    *rows_out = n;
     return 0;
 }

@@ -46,6 +46,7 @@ class _NumpyOnlyUnpickler(pickle.Unpickler):
         ("numpy", "ndarray"), ("numpy", "dtype"),
         ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
         ("numpy.core.numeric", "_frombuffer"), ("numpy._core.numeric", "_frombuffer"),
+        ("_codecs", "encode"),  # protocol <= 2 pickles carry the payload as latin-1 text
     }
 
     def find_class(self, module, name):
@@ -59,6 +60,16 @@ def decode_features(payload: bytes) -> np.ndarray:
     if payload[:6] == b"\x93NUMPY":
         return np.load(io.BytesIO(payload), allow_pickle=False)
     return _NumpyOnlyUnpickler(io.BytesIO(payload)).load()
+
+
+def _fast_tar():
+    """libwiseb200's host-side shard reader (wb_tar_scan / wb_tar_read) or None if the library is not built.
+    Reading shards is host logic, so the python tarfile reader below stays as the portable path."""
+    try:
+        from . import _capi
+        return _capi.lib(), _capi
+    except Exception:
+        return None
 
 
 class WebdatasetStore(FeatureStore):
@@ -141,7 +152,19 @@ class WebdatasetStore(FeatureStore):
         files = self.shard_files()
         self.feature_count = 0
         self.feature_dim = -1
+        self._shard_rows = {}
+        fast = _fast_tar() if os.environ.get("WISE_B200_FAST_STORE", "1") != "0" else None
         for fn in files:
+            if fast is not None:
+                import ctypes as C
+                rows, members, d = C.c_int64(), C.c_int64(), C.c_int64()
+                if fast[0].wb_tar_scan(fn.encode(), C.byref(rows), C.byref(members), C.byref(d)) == 0:
+                    # feature_count counts samples (tar members), like the reference; rows feed the index
+                    self.feature_count += members.value
+                    self._shard_rows[fn] = rows.value
+                    if self.feature_dim < 0 and d.value > 0:
+                        self.feature_dim = d.value
+                    continue
             with tarfile.open(fn) as tf:
                 for m in tf:
                     if not m.isreg():
@@ -181,8 +204,48 @@ class WebdatasetStore(FeatureStore):
     def __iter__(self):
         yield from self._maybe_shuffled()
 
+    def _fast_shards(self):
+        """Whole shards decoded by the C++ reader: yields (ids int64[n], x float32[n, d]) or None when a shard
+        needs the python reader.  Only for the un-shuffled, one-row-per-sample layout WISE writes."""
+        import ctypes as C
+        fast = _fast_tar()
+        for fn in self.shard_files():
+            rows = getattr(self, "_shard_rows", {}).get(fn)
+            if fast is None or rows is None or self.feature_dim <= 0:
+                yield fn, None
+                continue
+            ids = np.empty(rows, np.int64)
+            x = np.empty((rows, self.feature_dim), np.float32)
+            n = C.c_int64()
+            rc = fast[0].wb_tar_read(fn.encode(), self.feature_dim, rows, fast[1].ptr(ids), fast[1].ptr(x), C.byref(n))
+            yield fn, ((ids[: n.value], x[: n.value]) if rc == 0 else None)
+
     def iter_batch(self, batch_size=512):
-        """(ids int64[b], features float32[b, d]) batches; (1, d) samples squeezed like :131-139."""
+        """(ids int64[b], features float32[b, d]) batches; (1, d) samples squeezed like :131-139.
+        Un-shuffled reads go through the C++ shard reader (one pass per shard, no per-vector python objects)."""
+        if (not self.shard_shuffle and not self.shuffle_values and getattr(self, "_shard_rows", None)
+                and os.environ.get("WISE_B200_FAST_STORE", "1") != "0"):
+            carry_i, carry_x = None, None
+            for fn, dec in self._fast_shards():
+                if dec is None:  # this shard in python
+                    li, lx = [], []
+                    with tarfile.open(fn) as tf:
+                        for m in tf:
+                            key, _, ext = os.path.basename(m.name).partition(".")
+                            if m.isreg() and ext == "features.pyd":
+                                v = decode_features(tf.extractfile(m).read())
+                                li.append(int(key)); lx.append(np.squeeze(v, axis=0))
+                    dec = (np.asarray(li, np.int64), np.stack(lx).astype(np.float32)) if li else (np.empty(0, np.int64), np.empty((0, self.feature_dim), np.float32))
+                ids, x = dec
+                if carry_i is not None and carry_i.size:
+                    ids, x = np.concatenate([carry_i, ids]), np.concatenate([carry_x, x])
+                full = (ids.shape[0] // batch_size) * batch_size
+                for s in range(0, full, batch_size):
+                    yield ids[s:s + batch_size], x[s:s + batch_size]
+                carry_i, carry_x = ids[full:], x[full:]
+            if carry_i is not None and carry_i.size:
+                yield carry_i, carry_x
+            return
         ids, vecs = [], []
         for fid, vec in self._maybe_shuffled():
             ids.append(fid)
