@@ -34,7 +34,7 @@ inline bool scan_ndarray_pickle(const unsigned char* p, size_t n, Sample* out) {
     int ndim = -1;
     const unsigned char* best = nullptr;
     size_t best_len = 0;
-    bool f4 = false, last_bool = false, fortran = false;
+    bool f4 = false, last_bool = false, fortran = false, order_f = false;
     auto need = [&](size_t k) { return i + k <= n; };
     while (i < n) {
         const unsigned char op = p[i++];
@@ -43,6 +43,7 @@ inline bool scan_ndarray_pickle(const unsigned char* p, size_t n, Sample* out) {
             case 0x95: if (!need(8)) return false; i += 8; break;                             // FRAME
             case 0x8c: { if (!need(1)) return false; size_t l = p[i++]; if (!need(l)) return false;  // SHORT_BINUNICODE
                          if (l == 2 && p[i] == 'f' && p[i + 1] == '4') f4 = true;
+                         if (l == 1 && p[i] == 'F') order_f = true;  // _frombuffer(..., order='F') (proto 5)
                          i += l; nints = 0; break; }
             case 'X': { if (!need(4)) return false; uint32_t l; memcpy(&l, p + i, 4); i += 4; if (!need(l)) return false;
                         if (l == 2 && p[i] == 'f' && p[i + 1] == '4') f4 = true;
@@ -78,6 +79,8 @@ inline bool scan_ndarray_pickle(const unsigned char* p, size_t n, Sample* out) {
                         if (l >= best_len) { best = p + i; best_len = l; fortran = last_bool; } i += l; nints = 0; break; }
             case 'B': { if (!need(4)) return false; uint32_t l; memcpy(&l, p + i, 4); i += 4; if (!need(l)) return false;
                         if (l >= best_len) { best = p + i; best_len = l; fortran = last_bool; } i += l; nints = 0; break; }
+            case 0x96: { if (!need(8)) return false; uint64_t l; memcpy(&l, p + i, 8); i += 8; if (!need(l)) return false;  // BYTEARRAY8 (proto 5)
+                         if (l >= best_len) { best = p + i; best_len = (size_t)l; fortran = last_bool; } i += l; nints = 0; break; }
             case 0x8e: { if (!need(8)) return false; uint64_t l; memcpy(&l, p + i, 8); i += 8; if (!need(l)) return false;
                          if (l >= best_len) { best = p + i; best_len = (size_t)l; fortran = last_bool; } i += l; nints = 0; break; }
             case 'T': { if (!need(4)) return false; uint32_t l; memcpy(&l, p + i, 4); i += 4; if (!need(l)) return false;  // BINSTRING (proto 2 data)
@@ -88,7 +91,7 @@ inline bool scan_ndarray_pickle(const unsigned char* p, size_t n, Sample* out) {
         }
     }
     // the boolean right before the data bytes is the state tuple's is_fortran flag
-    if (!best || !f4 || fortran || ndim < 1) return false;
+    if (!best || !f4 || fortran || order_f || ndim < 1) return false;
     if (ndim == 1) { shape[1] = shape[0]; shape[0] = 1; }  // a bare (d,) vector counts as one row
     if (shape[0] <= 0 || shape[1] <= 0 || (size_t)(shape[0] * shape[1] * 4) != best_len) return false;
     out->data = best;
