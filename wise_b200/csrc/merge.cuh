@@ -87,7 +87,9 @@ __device__ __forceinline__ void block_select_topk(uint64_t* buf, int S, int k, i
 template <class Load2>
 __device__ __forceinline__ bool block_select_topk_lists(uint64_t* buf, int S, int k, int nlists, Load2 load, int* cnt) {
     const int tid = threadIdx.x;
-    const int j0 = min(k, max(1, S / max(nlists, 1)));
+    // round 0 depth: ~4x the expected share of a list in the global top-k (+ slack), at most what fits
+    const int j_fit = max(1, S / max(nlists, 1));
+    const int j0 = min(k, min(j_fit, max(4, (4 * k + nlists - 1) / max(nlists, 1) + 3)));
     const int n0 = nlists * j0;
     if (n0 > S) return false;  // more lists than buffer entries (uniform)
     for (int i = tid; i < S; i += kMergeThreads) buf[i] = i < n0 ? load(i / j0, i % j0) : 0ull;
