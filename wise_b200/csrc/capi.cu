@@ -506,7 +506,7 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_done[dev]) {
-        CK(cudaFuncSetAttribute(gemm_topk_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+        CK(cudaFuncSetAttribute(gemm_topk_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
         if (dev < 64) attr_done[dev] = true;
     }
     TRY(merge_smem_optin<true>());
@@ -553,7 +553,7 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
         g.row_end = r1;
         const int64_t nwork = ((r1 - r0 + kGemmBM - 1) / kGemmBM) * nqb;
         const unsigned grid = (unsigned)std::min<int64_t>(nwork, h->sm_count);
-        gemm_topk_kernel<BN><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
+        gemm_topk_kernel<BN, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
         CK(cudaGetLastError());
         const bool last = r1 >= nrows;
         c.D = last ? D : nullptr;
@@ -582,6 +582,62 @@ static int run_flat_gemm(wb_index* h, const float* rows, int64_t nrows, const fl
     if ((nq <= 64 && bn_max >= 64) || bn_max < 128)
         return run_flat_gemm_t<64>(h, rows, nrows, q_ld, nq, k, cap, ids, D, I, st, timed, overflowed);
     return run_flat_gemm_t<128>(h, rows, nrows, q_ld, nq, k, cap, ids, D, I, st, timed, overflowed);
+}
+
+// K4/K6 on the tensor cores: argmax over the centroid table for n device-resident points (row stride ld).
+// One launch, no epochs, no host synchronisation: the points are the A operand (streamed once from HBM), the
+// centroids are the query images (L2 resident), each row keeps its running maximum in the epilogue.
+static bool assign_gemm_eligible(const wb_index* h, int64_t n) {
+    return env_int("WB_GEMM", 1) != 0 && env_int("WB_GEMM_ASSIGN", 1) != 0 && n >= 1024 && h->nlist >= 64 &&
+           n < ((int64_t)1 << 31) - 256;
+}
+
+static int run_assign_gemm(wb_index* h, const float* x_ld, int64_t n, int32_t* assign_out, float* best_out,
+                           cudaStream_t st) {
+    constexpr int BN = 128;
+    using Cfg = GemmCfg<BN>;
+    const int ld = h->ld;
+    const int nchunks = (ld + kGemmBK - 1) / kGemmBK;
+    const int nqb = (int)((h->nlist + BN - 1) / BN);
+    TRY(h->gimg.ensure((size_t)nqb * nchunks * Cfg::kBBytes));
+    const int64_t n2 = (int64_t)nqb * nchunks * 8 * BN;
+    split_queries_kernel<BN><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(h->centroids, (int)h->nlist, ld, nchunks, nqb,
+                                                                          h->gimg.as<float>());
+    CK(cudaGetLastError());
+    PFN_encodeTiled encode = nullptr;
+    TRY(get_tensormap_encoder(&encode));
+    CUtensorMap tmap;
+    cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)n};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)kGemmBM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)x_ld, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    static thread_local bool attr_done[64] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_done[dev]) {
+        CK(cudaFuncSetAttribute(gemm_topk_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+        if (dev < 64) attr_done[dev] = true;
+    }
+    GemmParams g{};
+    g.row_begin = 0;
+    g.row_end = n;
+    g.nchunks = nchunks;
+    g.nq = (int)h->nlist;
+    g.nqb = nqb;
+    g.bimg = h->gimg.as<float>();
+    g.debug_terms = 3;
+    g.assign_out = assign_out;
+    g.best_out = best_out;
+    const int64_t ntiles = (n + kGemmBM - 1) / kGemmBM;
+    gemm_topk_kernel<BN, true><<<(unsigned)std::min<int64_t>(ntiles, h->sm_count), kGemmThreads, Cfg::kSmemBytes, st>>>(tmap, g);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    h->gemm_launches++;
+    return 0;
 }
 
 static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const float* q_dev, int64_t nq, int k,
@@ -650,6 +706,7 @@ static int ensure_csr(wb_index* h) {
 // assign rows [n0, n0+n) of the store to their max-inner-product centroid (K4 with k = 1)
 static int assign_rows(wb_index* h, const float* x_dev, int64_t n, int32_t* assign_out, float* best_out,
                        cudaStream_t st) {
+    if (assign_gemm_eligible(h, n)) return run_assign_gemm(h, x_dev, n, assign_out, best_out, st);
     TRY(h->pD.ensure((size_t)n * sizeof(float)));
     TRY(h->pI.ensure((size_t)n * sizeof(int64_t)));
     float* D = best_out ? best_out : h->pD.as<float>();

@@ -73,6 +73,10 @@ struct GemmParams {
     int nq;                       // real queries
     int nqb;                      // query blocks of BN queries
     int debug_terms;              // timing experiments only: number of split terms issued (3 = correct)
+    // ARGMAX mode (K4 add-time assignment, K6 k-means assignment): rows = points, queries = centroids;
+    // each row keeps a running (max score, lowest index) over all query blocks - no candidate lists.
+    int32_t* assign_out;          // [rows] argmax query index
+    float* best_out;              // [rows] its score
     const float* bimg;            // [nqb][nchunks][2][8][BN][4] pre-split query images
     const float* thr;             // [nqb*BN] current k-th best score per query (+inf for padding)
     uint64_t* keys;               // [nq][kstride]: [0,k) current top-k, [k, k+cap) candidates
@@ -193,7 +197,7 @@ __global__ void init_gemm_state_kernel(float* thr, int nq, int nq_pad, int* cnt,
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool ARGMAX>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
@@ -219,6 +223,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (p.row_end - p.row_begin + kGemmBM - 1) / kGemmBM;
     const int64_t nwork = ntiles * p.nqb;
+    // Work items (row tile, query block) of this CTA.  Search mode interleaves (tile, block) pairs over the CTAs
+    // (neighbouring CTAs share a row tile in L2); ARGMAX mode gives a CTA whole tiles and walks all query blocks
+    // of a tile back to back, so the per-row running maximum lives in the epilogue threads' registers.
+    const int64_t my_tiles = ntiles > (int64_t)blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t my_work =
+        ARGMAX ? my_tiles * p.nqb : (nwork > (int64_t)blockIdx.x ? (nwork - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+    auto work_at = [&](int64_t it, int64_t& tile, int& qb) {
+        if (ARGMAX) {
+            const int64_t t = it / p.nqb;
+            tile = blockIdx.x + t * gridDim.x;
+            qb = (int)(it - t * p.nqb);
+        } else {
+            const int64_t w = blockIdx.x + it * (int64_t)gridDim.x;
+            tile = w / p.nqb;
+            qb = (int)(w - tile * p.nqb);
+        }
+    };
 
     if (tid == 0) {
         for (int s = 0; s < kRaw; ++s) {
@@ -252,8 +273,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         {   // the whole warp runs the control flow (converged); one elected lane issues
             int s = 0;
             uint32_t ph = 0;
-            for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
-                const int64_t tile = w / p.nqb;
+            for (int64_t it = 0; it < my_work; ++it) {
+                int64_t tile;
+                int qb;
+                work_at(it, tile, qb);
                 const int row0 = (int)(p.row_begin + tile * kGemmBM);
                 for (int c = 0; c < p.nchunks; ++c) {
                     mbar_wait(&raw_empty[s], ph ^ 1u);
@@ -271,8 +294,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         {
             int s = 0;
             uint32_t ph = 0;
-            for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
-                const int qb = (int)(w % p.nqb);
+            for (int64_t it = 0; it < my_work; ++it) {
+                int64_t tile;
+                int qb;
+                work_at(it, tile, qb);
                 const float* bsrc = p.bimg + (size_t)qb * p.nchunks * (kBBytes / 4);
                 for (int c = 0; c < p.nchunks; ++c) {
                     mbar_wait(&slot_empty[s], ph ^ 1u);
@@ -294,7 +319,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             uint32_t ph = 0;
             int buf = 0;
             uint32_t dph = 0;
-            for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+            for (int64_t it = 0; it < my_work; ++it) {
                 mbar_wait(&d_empty[buf], dph ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
@@ -334,7 +359,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
         int64_t g = 0;                      // running chunk number over all work items of this CTA
-        for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+        for (int64_t it = 0; it < my_work; ++it) {
             for (int c = 0; c < p.nchunks; ++c, ++g) {
                 if ((g & 1) != set) continue;
                 const int sr = (int)(g % kRaw);
@@ -378,13 +403,21 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         const int etid = tid - 8 * 32;
         int buf = 0;
         uint32_t dph = 0;
-        for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
-            const int64_t tile = w / p.nqb;
-            const int qb = (int)(w - tile * p.nqb);
+        float best = -INFINITY;  // ARGMAX: running maximum of this thread's row over the query blocks
+        int best_i = 0;
+        for (int64_t it = 0; it < my_work; ++it) {
+            int64_t tile;
+            int qb;
+            work_at(it, tile, qb);
             const int64_t row = p.row_begin + tile * kGemmBM + quarter * 32 + lane;
             const bool row_ok = row < p.row_end;
-            if (etid < BN) thr_s[buf * BN + etid] = p.thr[qb * BN + etid];
-            named_bar_sync(kBarEpilogue, 128);
+            if constexpr (!ARGMAX) {
+                if (etid < BN) thr_s[buf * BN + etid] = p.thr[qb * BN + etid];
+                named_bar_sync(kBarEpilogue, 128);
+            } else if (qb == 0) {
+                best = -INFINITY;
+                best_i = 0;
+            }
             mbar_wait(&d_full[buf], dph);
             tc_fence_after();
             const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
@@ -393,28 +426,48 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                 uint32_t v[32];
                 tmem_ld32(td + cb * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if constexpr (ARGMAX) {
+                    const int q0 = qb * BN + cb * 32;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float sc = __uint_as_float(v[j]);
-                    const bool pass = row_ok && sc > thr_s[buf * BN + cb * 32 + j];
-                    const unsigned m = __ballot_sync(0xffffffffu, pass);
-                    if (m) {
-                        const int qi = qb * BN + cb * 32 + j;  // < nq: padded queries have thr = +inf
-                        int base = 0;
-                        if (lane == (__ffs(m) - 1)) base = atomicAdd(&p.cnt[qi], __popc(m));
-                        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                        if (pass) {
-                            const int slot = base + __popc(m & ((1u << lane) - 1));
-                            if (slot < p.cap) p.keys[(size_t)qi * p.kstride + p.k + slot] = make_key(sc, (uint32_t)row);
-                            else *p.overflow = 1;
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __uint_as_float(v[j]);
+                        // columns are visited in ascending index order: strict '>' keeps the lowest index on ties;
+                        // padded columns (index >= nq) hold zeros and must not win
+                        if (q0 + j < p.nq && sc > best) {
+                            best = sc;
+                            best_i = q0 + j;
                         }
                     }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __uint_as_float(v[j]);
+                        const bool pass = row_ok && sc > thr_s[buf * BN + cb * 32 + j];
+                        const unsigned m = __ballot_sync(0xffffffffu, pass);
+                        if (m) {
+                            const int qi = qb * BN + cb * 32 + j;  // < nq: padded queries have thr = +inf
+                            int base = 0;
+                            if (lane == (__ffs(m) - 1)) base = atomicAdd(&p.cnt[qi], __popc(m));
+                            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                            if (pass) {
+                                const int slot = base + __popc(m & ((1u << lane) - 1));
+                                if (slot < p.cap) p.keys[(size_t)qi * p.kstride + p.k + slot] = make_key(sc, (uint32_t)row);
+                                else *p.overflow = 1;
+                            }
+                        }
+                    }
+                }
+            }
+            if constexpr (ARGMAX) {
+                if (qb == p.nqb - 1 && row_ok) {
+                    p.assign_out[row] = best_i;
+                    if (p.best_out) p.best_out[row] = best;
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d_empty[buf]);
-            named_bar_sync(kBarEpilogue, 128);  // thr_s[buf] may be rewritten two tiles later
+            if constexpr (!ARGMAX) named_bar_sync(kBarEpilogue, 128);  // thr_s[buf] may be rewritten two tiles later
             if (++buf == 2) { buf = 0; dph ^= 1u; }
         }
     }
