@@ -106,6 +106,9 @@ int wb_exch_local_handle(wb_exchange* ex, void* handle64 /* 64 bytes out */);
 int wb_exch_open_peers(wb_exchange* ex, const void* handles /* [world][64] */);
 int wb_exch_merge_dev(wb_exchange* ex, int64_t nq, int64_t k, const float* D_local_dev, const int64_t* I_local_dev,
                       float* D_dev, int64_t* I_dev, void* stream);
+/* index.search(x, k) on a row-sharded index, host buffers in and out (every rank passes the same queries). */
+int wb_exch_search(wb_index* h, wb_exchange* ex, int64_t nq, const float* q_host, int64_t k, int64_t nprobe,
+                   float* D_host, int64_t* I_host);
 int wb_exch_free(wb_exchange* ex);
 
 /* ---- row access ------------------------------------------------------------------------- */

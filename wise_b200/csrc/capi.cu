@@ -95,7 +95,7 @@ struct wb_index {
     int64_t* list_off = nullptr;  // [nlist + 1]
     bool csr_dirty = true;
     // scratch
-    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gkeys, gstate;
+    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gkeys, gstate, eD, eI;
     int64_t gemm_launches = 0, gemm_fallbacks = 0;
     // device properties
     int sm_count = 148;
@@ -168,7 +168,7 @@ extern "C" int wb_free(wb_index* h) {
     cudaFree(h->perm);
     cudaFree(h->list_off);
     for (DevBuf* b : {&h->parts, &h->qbuf, &h->dbuf, &h->ibuf, &h->pD, &h->pI, &h->xbuf, &h->idbuf, &h->misc,
-                      &h->kperm, &h->koff, &h->gimg, &h->gkeys, &h->gstate})
+                      &h->kperm, &h->koff, &h->gimg, &h->gkeys, &h->gstate, &h->eD, &h->eI})
         b->release();
     for (int i = 0; i < wb_index::kEvRing; ++i) {
         cudaEventDestroy(h->ev0[i]);
@@ -1312,5 +1312,29 @@ extern "C" int wb_tar_read(const char* path, int64_t d, int64_t cap, int64_t* id
     }, &why);
     if (rc) return fail("wb_tar_read(%s): %s (code %d)", path, why.c_str(), rc), rc + 1;
     *rows_out = n;
+    return 0;
+}
+
+// Host-buffer search over a sharded index: H2D of the queries, local search, NVLink exchange + merge, D2H of the
+// global (D, I) - one call, one stream, one synchronisation.  Every rank calls it with the same queries.
+extern "C" int wb_exch_search(wb_index* h, wb_exchange* ex, int64_t nq, const float* q_host, int64_t k, int64_t nprobe,
+                              float* D_host, int64_t* I_host) {
+    TRY(check_search_args(h, nq, q_host, k, D_host, I_host));
+    if (!ex) return fail("NULL exchange");
+    if (nq == 0) return 0;
+    if (ex->device != h->device) return fail("index and exchange live on different devices");
+    TRY(set_dev(h));
+    cudaStream_t st = h->stream;
+    const float* q = nullptr;
+    TRY(stage_queries(h, nq, q_host, true, st, &q));
+    TRY(h->dbuf.ensure((size_t)nq * k * sizeof(float)));
+    TRY(h->ibuf.ensure((size_t)nq * k * sizeof(int64_t)));
+    TRY(h->eD.ensure((size_t)nq * k * sizeof(float)));
+    TRY(h->eI.ensure((size_t)nq * k * sizeof(int64_t)));
+    TRY(search_dev_impl(h, nq, q, k, nprobe, h->dbuf.as<float>(), h->ibuf.as<int64_t>(), st));
+    TRY(wb_exch_merge_dev(ex, nq, k, h->dbuf.as<float>(), h->ibuf.as<int64_t>(), h->eD.as<float>(), h->eI.as<int64_t>(), st));
+    CK(cudaMemcpyAsync(D_host, h->eD.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(I_host, h->eI.p, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return 0;
 }

@@ -149,6 +149,16 @@ class ShardedIndex:
 
     def search(self, x: np.ndarray, k: int):
         """faiss-style host API: numpy in, numpy out (same on every rank)."""
+        x = np.ascontiguousarray(x, np.float32)
+        if self.exchange is not None and self.exchange.fits(x.shape[0], int(k)):
+            # one C call: H2D, local search, NVLink exchange + merge, D2H (no torch ops on the path)
+            from . import _capi
+            nq = x.shape[0]
+            D = np.empty((nq, int(k)), np.float32)
+            I = np.empty((nq, int(k)), np.int64)
+            _capi.check(_capi.lib().wb_exch_search(self.local._h, self.exchange.h, nq, _capi.ptr(x), int(k),
+                                                  int(getattr(self.local, "nprobe", 1)), _capi.ptr(D), _capi.ptr(I)))
+            return D, I
         dev = self._comm_device()
         q = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(dev)
         nprobe = getattr(self.local, "nprobe", 1)
