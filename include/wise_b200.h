@@ -83,7 +83,9 @@ int wb_kmeans_update_dev(wb_index* h, const float* sums_dev, const int64_t* coun
 
 /* ---- search ----------------------------------------------------------------------------- */
 /* dist, ids = index.search(x, k)   feature_search_index.py:113, api/routes.py:1407.
- * nprobe is ignored by flat indices (index.nprobe, api/routes.py:899-902). 1 <= k <= WB_MAX_K. */
+ * nprobe is ignored by flat indices (index.nprobe, api/routes.py:899-902). 1 <= k <= WB_MAX_K.
+ * Batches of 5+ queries take the tensor-core path, which synchronises `stream` once at the end (it has to
+ * read the candidate-overflow flag); smaller batches and IVF list scans stay fully asynchronous in _dev. */
 int wb_search(wb_index* h, int64_t nq, const float* q_host, int64_t k, int64_t nprobe,
               float* D_host, int64_t* I_host);
 int wb_search_dev(wb_index* h, int64_t nq, const float* q_dev, int64_t k, int64_t nprobe,

@@ -94,6 +94,7 @@ struct wb_index {
     int64_t perm_cap = 0;
     int64_t* list_off = nullptr;  // [nlist + 1]
     bool csr_dirty = true;
+    bool contiguous = false;  // rows physically grouped by list (perm is the identity and not stored)
     // scratch
     DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gkeys, gstate, eD, eI;
     int64_t gemm_launches = 0, gemm_fallbacks = 0;
@@ -683,6 +684,10 @@ static int build_csr_host(const int32_t* assign_dev, int64_t n, int64_t nlist, s
     return 0;
 }
 
+// Build the inverted lists.  Default: PHYSICALLY group the row store by list (rows of a list become one
+// contiguous span, insertion order kept inside a list), so the list scan is a sequential HBM stream instead of
+// a gather of 2-3 KB rows (measured 3.3-4.3 TB/s gathered).  Needs a second copy of the rows while it runs; if
+// that does not fit, the lists stay a CSR of row indices over the insertion-ordered store.
 static int ensure_csr(wb_index* h) {
     if (!h->csr_dirty) return 0;
     std::vector<uint32_t> perm;
@@ -698,6 +703,38 @@ static int ensure_csr(wb_index* h) {
     CK(cudaMemcpyAsync(h->list_off, off.data(), (size_t)(h->nlist + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
                        h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->contiguous = false;
+    if (h->n > 0 && env_int("WB_IVF_CONTIGUOUS", 1)) {
+        const int64_t ncap = std::max<int64_t>(h->n, 1024);
+        const size_t need = (size_t)ncap * h->ld * 4 + (size_t)ncap * 12;
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        if (free_b > need + ((size_t)1 << 30)) {
+            float* nrows = nullptr;
+            int64_t* nids = nullptr;
+            int32_t* nas = nullptr;
+            CK(cudaMalloc(&nrows, (size_t)ncap * h->ld * 4));
+            CK(cudaMalloc(&nids, (size_t)ncap * 8));
+            CK(cudaMalloc(&nas, (size_t)ncap * 4));
+            const int ld4 = h->ld / 4;
+            const int64_t tot = h->n * ld4;
+            permute_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
+                reinterpret_cast<const float4*>(h->rows), reinterpret_cast<float4*>(nrows), h->perm, h->n, ld4);
+            CK(cudaGetLastError());
+            permute_ids_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->ids, nids, h->assign, nas, h->perm, h->n);
+            CK(cudaGetLastError());
+            h->launches += 2;
+            CK(cudaStreamSynchronize(h->stream));
+            cudaFree(h->rows);
+            cudaFree(h->ids);
+            cudaFree(h->assign);
+            h->rows = nrows;
+            h->ids = nids;
+            h->assign = nas;
+            h->cap = ncap;
+            h->contiguous = true;
+        }
+    }
     h->csr_dirty = false;
     return 0;
 }
@@ -801,7 +838,7 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
     p.ld = h->ld;
     p.k = (int)k;
     p.nparts = (int)S;
-    p.perm = h->perm;
+    p.perm = h->contiguous ? nullptr : h->perm;
     p.list_off = h->list_off;
     p.nprobe = np;
     const int evs = (int)(h->ev_count % wb_index::kEvRing);

@@ -218,6 +218,24 @@ __global__ void pad_rows_kernel(const float* src, float* dst, int64_t n, int d, 
     }
 }
 
+// dst[r, :] <- src[perm[r], :] in float4 units (IVF: group the row store by list)
+__global__ void permute_rows_kernel(const float4* src, float4* dst, const uint32_t* perm, int64_t n, int ld4) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n * ld4) {
+        const int64_t r = i / ld4;
+        const int c = (int)(i - r * ld4);
+        dst[i] = src[(size_t)perm[r] * ld4 + c];
+    }
+}
+__global__ void permute_ids_kernel(const int64_t* ids, int64_t* ids_out, const int32_t* asg, int32_t* asg_out,
+                                   const uint32_t* perm, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        ids_out[i] = ids[perm[i]];
+        asg_out[i] = asg[perm[i]];
+    }
+}
+
 // out[m, d] <- rows[pos[m], 0:d]
 __global__ void gather_rows_kernel(const float* rows, int ld, int d, const int64_t* pos, int64_t m, float* out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

@@ -49,7 +49,7 @@ struct ScanParams {
     uint64_t* parts;        // [nq][nparts][k] keys
     int nparts;             // == gridDim.x
     // gather mode (IVF): candidates = concatenation of the probed lists of query blockIdx.y
-    const uint32_t* perm;     // CSR: row index per slot
+    const uint32_t* perm;     // CSR: row index per slot; null when the rows are physically grouped by list
     const int64_t* list_off;  // CSR: [nlist + 1]
     const int64_t* probes;    // [nq][nprobe] list ids (-1 = none)
     int nprobe;
@@ -116,7 +116,8 @@ __device__ __forceinline__ uint32_t gather_row(const GatherCtx& G, uint32_t cpos
         if (G.prefix[mid] <= cpos) lo = mid;
         else hi = mid - 1;
     }
-    return G.perm[G.pbase[lo] + (int64_t)(cpos - G.prefix[lo])];
+    const int64_t slot = G.pbase[lo] + (int64_t)(cpos - G.prefix[lo]);
+    return G.perm ? G.perm[slot] : (uint32_t)slot;  // perm == null: rows are physically grouped by list
 }
 
 template <int NQ, int RW, bool GATHER>
@@ -231,6 +232,17 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                 float* dst = ring + (size_t)s * stage_floats;
                 if (!GATHER && p.single_copy) {
                     if (lane == 0) bulk_g2s(dst, src, cbytes * (uint32_t)nvalid, &full[s]);
+                } else if (GATHER && p.perm == nullptr && p.nchunks == 1) {
+                    // rows are grouped by list: consecutive candidates are consecutive rows except at a list
+                    // boundary, so each RUN of the group is one sequential copy (usually 1-2 per group)
+                    const int64_t prev = __shfl_up_sync(0xffffffffu, row, 1);
+                    const bool start = lane < nvalid && (lane == 0 || row != prev + 1);
+                    const unsigned sm = __ballot_sync(0xffffffffu, start);
+                    if (start) {
+                        const unsigned higher = sm & ~((2u << lane) - 1u);
+                        const int end = higher ? __ffs(higher) - 1 : nvalid;
+                        bulk_g2s(dst + (size_t)lane * ck, src, cbytes * (uint32_t)(end - lane), &full[s]);
+                    }
                 } else if (lane < nvalid) {
                     bulk_g2s(dst + (size_t)lane * ck, src + (size_t)ch * ck, cbytes, &full[s]);
                 }
