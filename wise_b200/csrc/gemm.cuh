@@ -479,4 +479,356 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
     }
 }
 
+// =====================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256-row x 128-query tile.
+// Each CTA keeps ITS 128 rows (raw ring, transform, A operand in its TMEM, accumulator in its TMEM, epilogue)
+// and only HALF of the query image (64 queries) in shared memory; the leader CTA issues one
+// tcgen05.mma.cta_group::2 (M = 256) per term and both SMs' tensor cores execute it, each fetching the
+// other half of B from its peer.  That halves the per-SM shared-memory traffic of the query operand
+// (B reads 64 -> 32 B/cycle, image writes 32 -> 16 KB per chunk), which is what capped the 1-CTA kernel
+// at ~72 % tensor-pipe activity (profiles/r01/gemm_experiments.md).
+// Cross-CTA protocol: the peer's transform / epilogue warps arrive on the LEADER's a_full / d_empty barriers
+// (mapa + mbarrier.arrive.shared::cluster), the peer's warp 1 forwards "my half image landed" to the leader's
+// bp_full, and the leader's tcgen05.commit multicasts slot_empty / d_full to both CTAs.
+constexpr int kG2BN = 128;
+constexpr int kG2Half = 64;
+constexpr int kG2BBytes = 2 * kG2Half * kGemmBK * 4;  // 16 KB: hi + lo image of this CTA's 64 queries
+constexpr int kG2ASlots = 4;   // A operand ring in TMEM (64 columns per slot)
+constexpr int kG2BSlots = 8;   // half-image ring in shared memory: deeper, it has to hide the cross-CTA forward
+constexpr int kG2Raw = (224 * 1024 - kG2BSlots * kG2BBytes) / kGemmABytes;  // 6
+constexpr int kG2NumBars = 2 * kG2Raw + 3 * kG2BSlots + 2 * kG2ASlots + 4;
+constexpr size_t kG2SmemBytes = 1024 + (size_t)kG2Raw * kGemmABytes + (size_t)kG2BSlots * kG2BBytes + kG2NumBars * 8 + 16 + 2 * kG2BN * 4;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
+    // default semantics (as CUTLASS' ClusterBarrier::arrive): an explicit .release.cluster costs an ERRBAR/MEMBAR per
+    // arrive, and what these arrivals publish (TMEM contents, async-proxy copies) is ordered by tcgen05 fences / the
+    // transaction barrier, not by generic-proxy release semantics
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// Waits on barriers that receive remote arrivals / multicast commits use the ordinary CTA-scope wait: polling with
+// .acquire.cluster makes every try_wait iteration invalidate L1 (CCTL.IVALL; 37 % of all stall samples, measured).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+
+template <bool ARGMAX>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
+    constexpr int BN = kG2BN;
+    constexpr int kRaw = kG2Raw;
+    constexpr int kASlots = kG2ASlots;
+    constexpr int kBSlots = kG2BSlots;
+    constexpr int kBBytes = kG2BBytes;
+    constexpr int kTmemAOff = 2 * BN;
+    extern __shared__ __align__(1024) unsigned char smem_gemm2[];
+    unsigned char* raw = smem_gemm2 + ((1024u - (smem_u32(smem_gemm2) & 1023u)) & 1023u);
+    unsigned char* bimg_s = raw + (size_t)kRaw * kGemmABytes;
+    uint64_t* raw_full = reinterpret_cast<uint64_t*>(bimg_s + (size_t)kBSlots * kBBytes);
+    uint64_t* raw_empty = raw_full + kRaw;
+    uint64_t* b_full = raw_empty + kRaw;      // my half image landed (local)
+    uint64_t* bp_full = b_full + kBSlots;     // leader only: the peer's half image landed
+    uint64_t* b_empty = bp_full + kBSlots;    // both: the MMAs that read this image slot have retired (multicast commit)
+    uint64_t* a_full = b_empty + kBSlots;     // leader only: A of BOTH CTAs is in TMEM (8 arrivals)
+    uint64_t* a_empty = a_full + kASlots;     // both: the MMAs that read this TMEM slot have retired (multicast commit)
+    uint64_t* d_full = a_empty + kASlots;     // both: accumulator ready (multicast commit)
+    uint64_t* d_empty = d_full + 2;           // leader only: both epilogues drained the accumulator (8 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+    float* thr_s = reinterpret_cast<float*>(tmem_slot + 2);  // [2][BN]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int64_t ntiles = (p.row_end - p.row_begin + kGemmBM - 1) / kGemmBM;
+    const int64_t ntp = (ntiles + 1) / 2;  // tile pairs
+    const int64_t nwork = ntp * p.nqb;
+    const int64_t my_tp = ntp > pair ? (ntp - pair + npairs - 1) / npairs : 0;
+    const int64_t my_work = ARGMAX ? my_tp * p.nqb : (nwork > pair ? (nwork - pair + npairs - 1) / npairs : 0);
+    auto work_at = [&](int64_t it, int64_t& tile, int& qb) {  // tile = THIS CTA's row tile
+        int64_t tp;
+        if (ARGMAX) {
+            const int64_t t = it / p.nqb;
+            tp = pair + t * npairs;
+            qb = (int)(it - t * p.nqb);
+        } else {
+            const int64_t w = pair + it * npairs;
+            tp = w / p.nqb;
+            qb = (int)(w - tp * p.nqb);
+        }
+        tile = 2 * tp + crank;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < kRaw; ++s) {
+            mbar_init(&raw_full[s], 1);
+            mbar_init(&raw_empty[s], 4);
+        }
+        for (int s = 0; s < kBSlots; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&bp_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < kASlots; ++s) {
+            mbar_init(&a_full[s], 8);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&d_full[b], 1);
+            mbar_init(&d_empty[b], 8);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== producer A: this CTA's raw row tiles =======================
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t it = 0; it < my_work; ++it) {
+            int64_t tile;
+            int qb;
+            work_at(it, tile, qb);
+            const int row0 = (int)(p.row_begin + tile * kGemmBM);  // may be past row_end: TMA zero-fills
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait(&raw_empty[s], ph ^ 1u);
+                if (elect_one_sync()) {
+                    mbar_arrive_expect_tx(&raw_full[s], kGemmABytes);
+                    tma_load_2d(raw + (size_t)s * kGemmABytes, &tmap, c * kGemmBK, row0, &raw_full[s]);
+                }
+                __syncwarp();
+                if (++s == kRaw) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 3) {
+        // =============================== producer B: this CTA's half of the query image =============
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t it = 0; it < my_work; ++it) {
+            int64_t tile;
+            int qb;
+            work_at(it, tile, qb);
+            const float* bsrc = p.bimg + (size_t)(2 * qb + (int)crank) * p.nchunks * (kBBytes / 4);  // images of 64 queries
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait_cluster(&b_empty[s], ph ^ 1u);
+                if (elect_one_sync()) {
+                    mbar_arrive_expect_tx(&b_full[s], kBBytes);
+                    bulk_g2s(bimg_s + (size_t)s * kBBytes, bsrc + (size_t)c * (kBBytes / 4), kBBytes, &b_full[s]);
+                }
+                __syncwarp();
+                if (++s == kBSlots) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && !leader) {
+        // =============================== peer: tell the leader when my half image has landed =========
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t it = 0; it < my_work; ++it) {
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait(&b_full[s], ph);
+                if (elect_one_sync()) mbar_arrive_cluster(&bp_full[s], 0);
+                __syncwarp();
+                if (++s == kBSlots) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== leader: MMA issuer for the pair ===============================
+        constexpr uint32_t idesc = umma_idesc_tf32(2 * kGemmBM, BN);
+        const uint64_t desc_hi0 = umma_smem_desc(smem_u32(bimg_s), kG2Half * 16, 128);  // my half: LBO = 64 * 16 B
+        int s = 0, sa = 0;
+        uint32_t ph = 0, pha = 0;
+        int buf = 0;
+        uint32_t dph = 0;
+        for (int64_t it = 0; it < my_work; ++it) {
+            mbar_wait_cluster(&d_empty[buf], dph ^ 1u);  // both epilogues have drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait(&b_full[s], ph);
+                mbar_wait_cluster(&bp_full[s], ph);
+                mbar_wait_cluster(&a_full[sa], pha);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t a_hi = tmem_base + (uint32_t)(kTmemAOff + sa * 64);
+                    const uint32_t a_lo = a_hi + 32;
+                    const uint64_t dh0 = desc_hi0 + (uint64_t)(((uint32_t)s * kBBytes) >> 4);
+                    const uint64_t dl0 = dh0 + (uint64_t)((kBBytes / 2) >> 4);
+#pragma unroll
+                    for (int j = 0; j < kGemmBK / 8; ++j) {
+                        const uint64_t dh = dh0 + (uint64_t)((j * 2 * kG2Half * 16) >> 4);
+                        const uint64_t dl = dl0 + (uint64_t)((j * 2 * kG2Half * 16) >> 4);
+                        umma_tf32_ts_2cta(d_tmem, a_hi + j * 8, dh, idesc, (c | j) != 0);
+                        umma_tf32_ts_2cta(d_tmem, a_hi + j * 8, dl, idesc, 1);
+                        umma_tf32_ts_2cta(d_tmem, a_lo + j * 8, dh, idesc, 1);
+                    }
+                    umma_commit_2cta(&b_empty[s]);
+                    umma_commit_2cta(&a_empty[sa]);
+                    if (c == p.nchunks - 1) umma_commit_2cta(&d_full[buf]);
+                }
+                __syncwarp();
+                if (++s == kBSlots) { s = 0; ph ^= 1u; }
+                if (++sa == kASlots) { sa = 0; pha ^= 1u; }
+            }
+            if (++buf == 2) { buf = 0; dph ^= 1u; }
+        }
+    } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+        // =============================== transform: fp32 -> (hi, lo) in this CTA's TMEM ================
+        const int set = warp >= 12 ? 1 : 0;
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        int64_t g = 0;
+        for (int64_t it = 0; it < my_work; ++it) {
+            for (int c = 0; c < p.nchunks; ++c, ++g) {
+                if ((g & 1) != set) continue;
+                const int sr = (int)(g % kRaw);
+                const uint32_t phr = (uint32_t)((g / kRaw) & 1);
+                const int ss = (int)(g % kASlots);
+                const uint32_t phs = (uint32_t)((g / kASlots) & 1);
+                mbar_wait(&raw_full[sr], phr);
+                const unsigned char* a_raw = raw + (size_t)sr * kGemmABytes + (size_t)r * 128;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const float4 v = *reinterpret_cast<const float4*>(a_raw + ((ch ^ (r & 7)) << 4));
+                    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t h = __float_as_uint(x[e]) & 0xFFFFE000u;
+                        hi[ch * 4 + e] = h;
+                        lo[ch * 4 + e] = __float_as_uint(x[e] - __uint_as_float(h));
+                    }
+                }
+                mbar_wait_cluster(&a_empty[ss], phs ^ 1u);
+                tc_fence_after();
+                const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kTmemAOff + ss * 64);
+                tmem_st32(ta, hi);
+                tmem_st32(ta + 32, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_cluster(&a_full[ss], 0);  // the leader counts 4 warps of each CTA
+                    mbar_arrive(&raw_empty[sr]);
+                }
+            }
+        }
+    } else if (warp >= 8 && warp < 12) {
+        // =============================== epilogue (this CTA's 128 rows) =================================
+        const int quarter = warp & 3;
+        const int etid = tid - 8 * 32;
+        int buf = 0;
+        uint32_t dph = 0;
+        float best = -INFINITY;
+        int best_i = 0;
+        for (int64_t it = 0; it < my_work; ++it) {
+            int64_t tile;
+            int qb;
+            work_at(it, tile, qb);
+            const int64_t row = p.row_begin + tile * kGemmBM + quarter * 32 + lane;
+            const bool row_ok = row < p.row_end;
+            if constexpr (!ARGMAX) {
+                if (etid < BN) thr_s[buf * BN + etid] = p.thr[qb * BN + etid];
+                named_bar_sync(kBarEpilogue, 128);
+            } else if (qb == 0) {
+                best = -INFINITY;
+                best_i = 0;
+            }
+            mbar_wait_cluster(&d_full[buf], dph);
+            tc_fence_after();
+            const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                uint32_t v[32];
+                tmem_ld32(td + cb * 32, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if constexpr (ARGMAX) {
+                    const int q0 = qb * BN + cb * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __uint_as_float(v[j]);
+                        if (q0 + j < p.nq && sc > best) {
+                            best = sc;
+                            best_i = q0 + j;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __uint_as_float(v[j]);
+                        const bool pass = row_ok && sc > thr_s[buf * BN + cb * 32 + j];
+                        const unsigned m = __ballot_sync(0xffffffffu, pass);
+                        if (m) {
+                            const int qi = qb * BN + cb * 32 + j;
+                            int base = 0;
+                            if (lane == (__ffs(m) - 1)) base = atomicAdd(&p.cnt[qi], __popc(m));
+                            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                            if (pass) {
+                                const int slot = base + __popc(m & ((1u << lane) - 1));
+                                if (slot < p.cap) p.keys[(size_t)qi * p.kstride + p.k + slot] = make_key(sc, (uint32_t)row);
+                                else *p.overflow = 1;
+                            }
+                        }
+                    }
+                }
+            }
+            if constexpr (ARGMAX) {
+                if (qb == p.nqb - 1 && row_ok) {
+                    p.assign_out[row] = best_i;
+                    if (p.best_out) p.best_out[row] = best;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&d_empty[buf], 0);
+            if constexpr (!ARGMAX) named_bar_sync(kBarEpilogue, 128);
+            if (++buf == 2) { buf = 0; dph ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's shared memory and TMEM stay alive until the leader's last MMA has retired
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
 }  // namespace wb
