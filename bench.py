@@ -292,11 +292,19 @@ def run_ours(a):
         sampler.start()
     # pre-roll (untimed, all ranks): keep the GPU under the same load for ~0.6 s so that nvidia-smi, which needs a
     # few hundred ms to start, has samples that bracket the timed region instead of one stray reading
+    # (the number of pre-roll searches must be the same on every rank: the exchange is a collective)
     qpre = make_queries(centres, a.batch, a.dim, 2024, device)
+    barrier()
     t_pre = time.perf_counter()
-    while time.perf_counter() - t_pre < 0.6:
+    for _ in range(3):
         sharded.search_dev(qpre, a.k)
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    t3 = torch.tensor([(time.perf_counter() - t_pre) / 3], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    for _ in range(int(min(2000, max(1, 0.6 / max(float(t3.item()), 1e-5))))):
+        sharded.search_dev(qpre, a.k)
+    torch.cuda.synchronize()
     ms_step, scan_ms, launches = timed_steps(a.batch, a.steps, a.warmup)
     clocks = sampler.finish() if sampler else None
     e2e_ms, D_last, I_last = timed_e2e(a.batch, a.steps, a.warmup)
