@@ -1,6 +1,6 @@
 #!/bin/bash
-for v in 0 1; do
-  echo "== WB_GEMM_2CTA=$v"
-  WB_GEMM_2CTA=$v timeout 300 python scripts/gpu_gemm.py time 2>&1 | grep -E "^nq=(128|256|1024)|FAIL" | cut -c1-150
+for c in "0 0" "0 1" "1 0" "1 1"; do
+  set -- $c
+  echo "== WB_GEMM_2CTA=$1 WB_GEMM_PREFETCH=$2"
+  WB_GEMM_2CTA=$1 WB_GEMM_PREFETCH=$2 timeout 300 python scripts/gpu_gemm.py time 2>&1 | grep -E "^nq=(16|64|128) |^nq=(16|64|128):|FAIL" | cut -c1-110
 done
-WB_GEMM_2CTA=1 timeout 120 python scripts/diag_gemm.py 2>&1 | grep -E "trial" | head -3

@@ -472,7 +472,7 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     const int nchunks = (ld + kGemmBK - 1) / kGemmBK;
     const int nqb = (int)((nq + kGemmBN - 1) / kGemmBN);
     const int kstride = k + cap;
-    const bool use2 = BN == 128 && env_int("WB_GEMM_2CTA", 1) != 0 && (h->sm_count % 2) == 0;
+    const bool use2 = env_int("WB_GEMM_2CTA", 1) != 0 && (h->sm_count % 2) == 0;
     TRY(h->gimg.ensure((size_t)nqb * nchunks * kGemmBBytes));
     TRY(h->gkeys.ensure((size_t)nq * kstride * sizeof(uint64_t)));
     TRY(h->gstate.ensure((size_t)nqb * kGemmBN * 4 + (size_t)nq * 4 + 64));
@@ -487,9 +487,9 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
         CK(cudaGetLastError());
         const int64_t n2 = (int64_t)nqb * nchunks * 8 * kGemmBN;
         if (use2) {  // the 2-CTA kernel wants one image per 64 queries (each CTA of a pair holds half a block)
-            const int64_t n3 = (int64_t)(2 * nqb) * nchunks * 8 * kG2Half;
-            split_queries_kernel<kG2Half><<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, 2 * nqb,
-                                                                                   h->gimg.as<float>());
+            const int64_t n3 = (int64_t)(2 * nqb) * nchunks * 8 * (BN / 2);
+            split_queries_kernel<BN / 2><<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, 2 * nqb,
+                                                                                  h->gimg.as<float>());
         } else {
             split_queries_kernel<BN><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb,
                                                                               h->gimg.as<float>());
@@ -529,6 +529,10 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     g.nqb = nqb;
     g.bimg = h->gimg.as<float>();
     g.debug_terms = env_int("WB_GEMM_DEBUG_TERMS", 3);
+    g.rows = rows;
+    g.ld = ld;
+    g.nrows_total = nrows;
+    g.prefetch = env_int("WB_GEMM_PREFETCH", 1);
     g.thr = thr;
     g.keys = keys;
     g.cnt = cnt;
@@ -564,12 +568,13 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
         if (use2) {
             static thread_local bool a2[64] = {};
             if (dev >= 64 || !a2[dev]) {
-                CK(cudaFuncSetAttribute(gemm2_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG2SmemBytes));
+                CK(cudaFuncSetAttribute(gemm2_topk_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)Gemm2Cfg<BN>::kSmemBytes));
                 if (dev < 64) a2[dev] = true;
             }
             const int64_t ntp = ((r1 - r0 + kGemmBM - 1) / kGemmBM + 1) / 2;
             const unsigned grid2 = 2u * (unsigned)std::min<int64_t>(ntp * nqb, h->sm_count / 2);
-            gemm2_topk_kernel<false><<<grid2, kGemmThreads, kG2SmemBytes, st>>>(tmap, g);
+            gemm2_topk_kernel<BN, false><<<grid2, kGemmThreads, Gemm2Cfg<BN>::kSmemBytes, st>>>(tmap, g);
         } else {
             gemm_topk_kernel<BN, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
         }
@@ -622,9 +627,9 @@ static int run_assign_gemm(wb_index* h, const float* x_ld, int64_t n, int32_t* a
     const int64_t n2 = (int64_t)nqb * nchunks * 8 * BN;
     const bool use2 = env_int("WB_GEMM_2CTA", 1) != 0 && (h->sm_count % 2) == 0;
     if (use2) {
-        const int64_t n3 = (int64_t)(2 * nqb) * nchunks * 8 * kG2Half;
-        split_queries_kernel<kG2Half><<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(h->centroids, (int)h->nlist, ld, nchunks,
-                                                                               2 * nqb, h->gimg.as<float>());
+        const int64_t n3 = (int64_t)(2 * nqb) * nchunks * 8 * (BN / 2);
+        split_queries_kernel<BN / 2><<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(h->centroids, (int)h->nlist, ld, nchunks,
+                                                                              2 * nqb, h->gimg.as<float>());
     } else {
         split_queries_kernel<BN><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(h->centroids, (int)h->nlist, ld, nchunks, nqb,
                                                                               h->gimg.as<float>());
@@ -662,11 +667,13 @@ static int run_assign_gemm(wb_index* h, const float* x_ld, int64_t n, int32_t* a
     if (use2) {
         static thread_local bool a2[64] = {};
         if (dev >= 64 || !a2[dev]) {
-            CK(cudaFuncSetAttribute(gemm2_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG2SmemBytes));
+            CK(cudaFuncSetAttribute(gemm2_topk_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)Gemm2Cfg<BN>::kSmemBytes));
             if (dev < 64) a2[dev] = true;
         }
         const int64_t ntp = (ntiles + 1) / 2;
-        gemm2_topk_kernel<true><<<2u * (unsigned)std::min<int64_t>(ntp, h->sm_count / 2), kGemmThreads, kG2SmemBytes, st>>>(tmap, g);
+        gemm2_topk_kernel<BN, true><<<2u * (unsigned)std::min<int64_t>(ntp, h->sm_count / 2), kGemmThreads,
+                                     Gemm2Cfg<BN>::kSmemBytes, st>>>(tmap, g);
     } else {
         gemm_topk_kernel<BN, true><<<(unsigned)std::min<int64_t>(ntiles, h->sm_count), kGemmThreads, Cfg::kSmemBytes, st>>>(tmap, g);
     }

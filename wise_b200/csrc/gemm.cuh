@@ -34,13 +34,6 @@
 
 #include "common.cuh"
 
-#ifndef WB_GEMM_ELECT_MMA
-#define WB_GEMM_ELECT_MMA 1
-#endif
-#ifndef WB_GEMM_ELECT_PROD
-#define WB_GEMM_ELECT_PROD 1
-#endif
-
 namespace wb {
 
 constexpr int kGemmBM = 128;      // database rows per tile (UMMA M)
@@ -73,6 +66,12 @@ struct GemmParams {
     int nq;                       // real queries
     int nqb;                      // query blocks of BN queries
     int debug_terms;              // timing experiments only: number of split terms issued (3 = correct)
+    // small batches (one query block): pull the NEXT row tile into L2 with sequential bulk prefetches while the
+    // current tile is processed - the 2-D tile loads read 128 B out of every row per chunk, a poor DRAM pattern
+    const float* rows;
+    int ld;
+    int64_t nrows_total;
+    int prefetch;
     // ARGMAX mode (K4 add-time assignment, K6 k-means assignment): rows = points, queries = centroids;
     // each row keeps a running (max score, lowest index) over all query blocks - no candidate lists.
     int32_t* assign_out;          // [rows] argmax query index
@@ -95,6 +94,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
             smem_u32(dst)),
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
+}
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -278,9 +281,25 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                 int qb;
                 work_at(it, tile, qb);
                 const int row0 = (int)(p.row_begin + tile * kGemmBM);
+                size_t pf_bytes = 0, pf_slice = 0;
+                const char* pf_base = nullptr;
+                if (p.prefetch && p.nqb == 1 && it + 1 < my_work) {
+                    int64_t t2;
+                    int q2;
+                    work_at(it + 1, t2, q2);
+                    const int64_t r2 = p.row_begin + t2 * kGemmBM;
+                    const int64_t nr = min((int64_t)kGemmBM, p.nrows_total - r2);
+                    if (nr > 0) {
+                        pf_bytes = (size_t)nr * p.ld * 4;
+                        pf_slice = ((pf_bytes + p.nchunks - 1) / p.nchunks + 15) & ~(size_t)15;
+                        pf_base = reinterpret_cast<const char*>(p.rows + (size_t)r2 * p.ld);
+                    }
+                }
                 for (int c = 0; c < p.nchunks; ++c) {
                     mbar_wait(&raw_empty[s], ph ^ 1u);
-                    if (WB_GEMM_ELECT_PROD ? elect_one_sync() : (lane == 0)) {
+                    if (elect_one_sync()) {
+                        if ((size_t)c * pf_slice < pf_bytes)
+                            bulk_prefetch_l2(pf_base + (size_t)c * pf_slice, (uint32_t)min(pf_slice, pf_bytes - (size_t)c * pf_slice));
                         mbar_arrive_expect_tx(&raw_full[s], kGemmABytes);
                         tma_load_2d(raw + (size_t)s * kGemmABytes, &tmap, c * kGemmBK, row0, &raw_full[s]);
                     }
@@ -301,7 +320,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                 const float* bsrc = p.bimg + (size_t)qb * p.nchunks * (kBBytes / 4);
                 for (int c = 0; c < p.nchunks; ++c) {
                     mbar_wait(&slot_empty[s], ph ^ 1u);
-                    if (WB_GEMM_ELECT_PROD ? elect_one_sync() : (lane == 0)) {
+                    if (elect_one_sync()) {
                         mbar_arrive_expect_tx(&b_full[s], kBBytes);
                         bulk_g2s(bimg_s + (size_t)s * kBBytes, bsrc + (size_t)c * (kBBytes / 4), kBBytes, &b_full[s]);
                     }
@@ -327,7 +346,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                     mbar_wait(&b_full[s], ph);  // query image landed
                     mbar_wait(&a_full[s], ph);  // A hi/lo written to TMEM
                     tc_fence_after();
-                    if (WB_GEMM_ELECT_MMA ? elect_one_sync() : (lane == 0)) {
+                    if (elect_one_sync()) {
                         const uint32_t a_hi = tmem_base + (uint32_t)(kTmemAOff + s * 64);
                         const uint32_t a_lo = a_hi + 32;
                         // descriptors differ only in the start-address field: add (bytes >> 4) to the low word
@@ -490,14 +509,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
 // Cross-CTA protocol: the peer's transform / epilogue warps arrive on the LEADER's a_full / d_empty barriers
 // (mapa + mbarrier.arrive.shared::cluster), the peer's warp 1 forwards "my half image landed" to the leader's
 // bp_full, and the leader's tcgen05.commit multicasts slot_empty / d_full to both CTAs.
-constexpr int kG2BN = 128;
-constexpr int kG2Half = 64;
-constexpr int kG2BBytes = 2 * kG2Half * kGemmBK * 4;  // 16 KB: hi + lo image of this CTA's 64 queries
 constexpr int kG2ASlots = 4;   // A operand ring in TMEM (64 columns per slot)
 constexpr int kG2BSlots = 8;   // half-image ring in shared memory: deeper, it has to hide the cross-CTA forward
-constexpr int kG2Raw = (224 * 1024 - kG2BSlots * kG2BBytes) / kGemmABytes;  // 6
-constexpr int kG2NumBars = 2 * kG2Raw + 3 * kG2BSlots + 2 * kG2ASlots + 4;
-constexpr size_t kG2SmemBytes = 1024 + (size_t)kG2Raw * kGemmABytes + (size_t)kG2BSlots * kG2BBytes + kG2NumBars * 8 + 16 + 2 * kG2BN * 4;
+template <int BN>              // BN = queries per block of the PAIR (32 / 64 / 128); each CTA holds BN / 2 of them
+struct Gemm2Cfg {
+    static constexpr int kHalf = BN / 2;
+    static constexpr int kBBytes = 2 * kHalf * kGemmBK * 4;  // hi + lo image of this CTA's queries (16 KB at BN = 128)
+    static constexpr int kRaw = (224 * 1024 - kG2BSlots * kBBytes) / kGemmABytes > 12
+                                    ? 12 : (224 * 1024 - kG2BSlots * kBBytes) / kGemmABytes;
+    static constexpr int kNumBars = 2 * kRaw + 3 * kG2BSlots + 2 * kG2ASlots + 4;
+    static constexpr size_t kSmemBytes =
+        1024 + (size_t)kRaw * kGemmABytes + (size_t)kG2BSlots * kBBytes + kNumBars * 8 + 16 + 2 * BN * 4;
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -540,14 +563,15 @@ __device__ __forceinline__ void umma_tf32_ts_2cta(uint32_t d_tmem, uint32_t a_tm
         : "memory");
 }
 
-template <bool ARGMAX>
+template <int BN, bool ARGMAX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
-    constexpr int BN = kG2BN;
-    constexpr int kRaw = kG2Raw;
+    using Cfg2 = Gemm2Cfg<BN>;
+    constexpr int kG2Half = Cfg2::kHalf;
+    constexpr int kRaw = Cfg2::kRaw;
     constexpr int kASlots = kG2ASlots;
     constexpr int kBSlots = kG2BSlots;
-    constexpr int kBBytes = kG2BBytes;
+    constexpr int kBBytes = Cfg2::kBBytes;
     constexpr int kTmemAOff = 2 * BN;
     extern __shared__ __align__(1024) unsigned char smem_gemm2[];
     unsigned char* raw = smem_gemm2 + ((1024u - (smem_u32(smem_gemm2) & 1023u)) & 1023u);
@@ -628,9 +652,25 @@ gemm2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) 
             int qb;
             work_at(it, tile, qb);
             const int row0 = (int)(p.row_begin + tile * kGemmBM);  // may be past row_end: TMA zero-fills
+            size_t pf_bytes = 0, pf_slice = 0;
+            const char* pf_base = nullptr;
+            if (p.prefetch && p.nqb == 1 && it + 1 < my_work) {
+                int64_t t2;
+                int q2;
+                work_at(it + 1, t2, q2);
+                const int64_t r2 = p.row_begin + t2 * kGemmBM;
+                const int64_t nr = min((int64_t)kGemmBM, p.nrows_total - r2);
+                if (nr > 0) {
+                    pf_bytes = (size_t)nr * p.ld * 4;
+                    pf_slice = ((pf_bytes + p.nchunks - 1) / p.nchunks + 15) & ~(size_t)15;
+                    pf_base = reinterpret_cast<const char*>(p.rows + (size_t)r2 * p.ld);
+                }
+            }
             for (int c = 0; c < p.nchunks; ++c) {
                 mbar_wait(&raw_empty[s], ph ^ 1u);
                 if (elect_one_sync()) {
+                    if ((size_t)c * pf_slice < pf_bytes)
+                        bulk_prefetch_l2(pf_base + (size_t)c * pf_slice, (uint32_t)min(pf_slice, pf_bytes - (size_t)c * pf_slice));
                     mbar_arrive_expect_tx(&raw_full[s], kGemmABytes);
                     tma_load_2d(raw + (size_t)s * kGemmABytes, &tmap, c * kGemmBK, row0, &raw_full[s]);
                 }
@@ -646,7 +686,7 @@ gemm2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) 
             int64_t tile;
             int qb;
             work_at(it, tile, qb);
-            const float* bsrc = p.bimg + (size_t)(2 * qb + (int)crank) * p.nchunks * (kBBytes / 4);  // images of 64 queries
+            const float* bsrc = p.bimg + (size_t)(2 * qb + (int)crank) * p.nchunks * (kBBytes / 4);  // images of BN/2 queries
             for (int c = 0; c < p.nchunks; ++c) {
                 mbar_wait_cluster(&b_empty[s], ph ^ 1u);
                 if (elect_one_sync()) {
@@ -672,7 +712,7 @@ gemm2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) 
     } else if (warp == 1) {
         // =============================== leader: MMA issuer for the pair ===============================
         constexpr uint32_t idesc = umma_idesc_tf32(2 * kGemmBM, BN);
-        const uint64_t desc_hi0 = umma_smem_desc(smem_u32(bimg_s), kG2Half * 16, 128);  // my half: LBO = 64 * 16 B
+        const uint64_t desc_hi0 = umma_smem_desc(smem_u32(bimg_s), kG2Half * 16, 128);  // my half: LBO = (BN/2) * 16 B
         int s = 0, sa = 0;
         uint32_t ph = 0, pha = 0;
         int buf = 0;
