@@ -472,7 +472,8 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     const int nchunks = (ld + kGemmBK - 1) / kGemmBK;
     const int nqb = (int)((nq + kGemmBN - 1) / kGemmBN);
     const int kstride = k + cap;
-    const bool use2 = env_int("WB_GEMM_2CTA", 1) != 0 && (h->sm_count % 2) == 0;
+    // measured (profiles/r01/gemm_experiments.md): the CTA pair wins from 64 queries up, the single CTA below
+    const bool use2 = BN >= 64 && env_int("WB_GEMM_2CTA", 1) != 0 && (h->sm_count % 2) == 0;
     TRY(h->gimg.ensure((size_t)nqb * nchunks * kGemmBBytes));
     TRY(h->gkeys.ensure((size_t)nq * kstride * sizeof(uint64_t)));
     TRY(h->gstate.ensure((size_t)nqb * kGemmBN * 4 + (size_t)nq * 4 + 64));
@@ -529,10 +530,6 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     g.nqb = nqb;
     g.bimg = h->gimg.as<float>();
     g.debug_terms = env_int("WB_GEMM_DEBUG_TERMS", 3);
-    g.rows = rows;
-    g.ld = ld;
-    g.nrows_total = nrows;
-    g.prefetch = env_int("WB_GEMM_PREFETCH", 1);
     g.thr = thr;
     g.keys = keys;
     g.cnt = cnt;

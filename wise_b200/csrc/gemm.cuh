@@ -66,12 +66,6 @@ struct GemmParams {
     int nq;                       // real queries
     int nqb;                      // query blocks of BN queries
     int debug_terms;              // timing experiments only: number of split terms issued (3 = correct)
-    // small batches (one query block): pull the NEXT row tile into L2 with sequential bulk prefetches while the
-    // current tile is processed - the 2-D tile loads read 128 B out of every row per chunk, a poor DRAM pattern
-    const float* rows;
-    int ld;
-    int64_t nrows_total;
-    int prefetch;
     // ARGMAX mode (K4 add-time assignment, K6 k-means assignment): rows = points, queries = centroids;
     // each row keeps a running (max score, lowest index) over all query blocks - no candidate lists.
     int32_t* assign_out;          // [rows] argmax query index
@@ -94,10 +88,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
             smem_u32(dst)),
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
-}
-
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -281,25 +271,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                 int qb;
                 work_at(it, tile, qb);
                 const int row0 = (int)(p.row_begin + tile * kGemmBM);
-                size_t pf_bytes = 0, pf_slice = 0;
-                const char* pf_base = nullptr;
-                if (p.prefetch && p.nqb == 1 && it + 1 < my_work) {
-                    int64_t t2;
-                    int q2;
-                    work_at(it + 1, t2, q2);
-                    const int64_t r2 = p.row_begin + t2 * kGemmBM;
-                    const int64_t nr = min((int64_t)kGemmBM, p.nrows_total - r2);
-                    if (nr > 0) {
-                        pf_bytes = (size_t)nr * p.ld * 4;
-                        pf_slice = ((pf_bytes + p.nchunks - 1) / p.nchunks + 15) & ~(size_t)15;
-                        pf_base = reinterpret_cast<const char*>(p.rows + (size_t)r2 * p.ld);
-                    }
-                }
                 for (int c = 0; c < p.nchunks; ++c) {
                     mbar_wait(&raw_empty[s], ph ^ 1u);
                     if (elect_one_sync()) {
-                        if ((size_t)c * pf_slice < pf_bytes)
-                            bulk_prefetch_l2(pf_base + (size_t)c * pf_slice, (uint32_t)min(pf_slice, pf_bytes - (size_t)c * pf_slice));
                         mbar_arrive_expect_tx(&raw_full[s], kGemmABytes);
                         tma_load_2d(raw + (size_t)s * kGemmABytes, &tmap, c * kGemmBK, row0, &raw_full[s]);
                     }
@@ -652,25 +626,9 @@ gemm2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) 
             int qb;
             work_at(it, tile, qb);
             const int row0 = (int)(p.row_begin + tile * kGemmBM);  // may be past row_end: TMA zero-fills
-            size_t pf_bytes = 0, pf_slice = 0;
-            const char* pf_base = nullptr;
-            if (p.prefetch && p.nqb == 1 && it + 1 < my_work) {
-                int64_t t2;
-                int q2;
-                work_at(it + 1, t2, q2);
-                const int64_t r2 = p.row_begin + t2 * kGemmBM;
-                const int64_t nr = min((int64_t)kGemmBM, p.nrows_total - r2);
-                if (nr > 0) {
-                    pf_bytes = (size_t)nr * p.ld * 4;
-                    pf_slice = ((pf_bytes + p.nchunks - 1) / p.nchunks + 15) & ~(size_t)15;
-                    pf_base = reinterpret_cast<const char*>(p.rows + (size_t)r2 * p.ld);
-                }
-            }
             for (int c = 0; c < p.nchunks; ++c) {
                 mbar_wait(&raw_empty[s], ph ^ 1u);
                 if (elect_one_sync()) {
-                    if ((size_t)c * pf_slice < pf_bytes)
-                        bulk_prefetch_l2(pf_base + (size_t)c * pf_slice, (uint32_t)min(pf_slice, pf_bytes - (size_t)c * pf_slice));
                     mbar_arrive_expect_tx(&raw_full[s], kGemmABytes);
                     tma_load_2d(raw + (size_t)s * kGemmABytes, &tmap, c * kGemmBK, row0, &raw_full[s]);
                 }
