@@ -550,7 +550,9 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     c.cnt = cnt;
     c.thr = thr;
     c.ids = ids;
-    const double growth = std::min(3.0, std::max(0.25, (double)cap / (4.0 * k)));
+    // next epoch = growth x (rows seen so far): a query then collects ~k*ln(1+growth) survivors per epoch, far
+    // below `cap`; fewer, larger epochs mean fewer launch gaps and compactions (each costs ~50 us)
+    const double growth = std::min(12.0, std::max(0.25, (double)cap / (4.0 * k)));
     const int evs = (int)(h->ev_count % wb_index::kEvRing);
     if (timed && h->timing) CK(cudaEventRecord(h->ev0[evs], st));
     int64_t r0 = 0;
