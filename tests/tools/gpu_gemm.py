@@ -1,6 +1,6 @@
 """Dev script: first contact of the tcgen05 path (K2) - parity vs the oracle, then timing."""
 import ctypes as C, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import oracle as O
 from wise_b200 import faiss_compat as faiss, _capi

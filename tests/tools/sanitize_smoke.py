@@ -1,6 +1,6 @@
 """Small end-to-end pass over every kernel for compute-sanitizer (memcheck / racecheck)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle import oracle as O
 from wise_b200 import faiss_compat as faiss
