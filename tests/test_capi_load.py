@@ -53,9 +53,10 @@ def test_compute_fails_loudly_without_gpu():
 
 
 def test_product_never_imports_oracle():
-    """oracle/ is test infrastructure: nothing under wise_b200/ may reference it."""
-    for dirpath, _, files in os.walk(os.path.join(ROOT, "wise_b200")):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                txt = open(os.path.join(dirpath, f)).read()
-                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+    """oracle/ is test infrastructure: nothing under wise_b200/ (or the measurement scripts) may reference it."""
+    for top in ("wise_b200", "scripts"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f

@@ -238,7 +238,8 @@ def _gemm_stats(idx):
 @pytest.mark.parametrize("n,d,nq,k,clustered", [
     (40000, 768, 16, 10, False), (40000, 768, 128, 10, False), (100000, 512, 200, 100, False),
     (50000, 100, 33, 5, False), (131072, 768, 300, 100, True), (70001, 1024, 64, 50, False),
-    (300000, 64, 1000, 10, False), (60000, 70, 129, 100, True), (200000, 768, 1024, 100, True)])
+    (300000, 64, 1000, 10, False), (60000, 70, 129, 100, True), (200000, 768, 1024, 100, True),
+    (300000, 32, 10, 2048, False), (270000, 48, 40, 1000, True), (99999, 260, 65, 7, False)])
 def test_gemm_path_matches_oracle(faiss, n, d, nq, k, clustered):
     """3xTF32 on tcgen05: scores within 1e-5 of the fp64 oracle (observed ~1.5e-6), ids identical outside
     near-tie bands; the band is widened to 4e-6 here because the tensor-core accumulation noise is ~1.5e-6."""
