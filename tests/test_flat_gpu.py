@@ -240,9 +240,10 @@ def _gemm_stats(idx):
     (50000, 100, 33, 5, False), (131072, 768, 300, 100, True), (70001, 1024, 64, 50, False),
     (300000, 64, 1000, 10, False), (60000, 70, 129, 100, True), (200000, 768, 1024, 100, True),
     (300000, 32, 10, 2048, False), (270000, 48, 40, 1000, True), (99999, 260, 65, 7, False)])
-def test_gemm_path_matches_oracle(faiss, n, d, nq, k, clustered):
-    """3xTF32 on tcgen05: scores within 1e-5 of the fp64 oracle (observed ~1.5e-6), ids identical outside
+def test_gemm_path_matches_oracle(faiss, monkeypatch, n, d, nq, k, clustered):
+    """WB_GEMM_FORCE=1 bypasses the size heuristic so that small stores exercise K2 too.  3xTF32 on tcgen05: scores within 1e-5 of the fp64 oracle (observed ~1.5e-6), ids identical outside
     near-tie bands; the band is widened to 4e-6 here because the tensor-core accumulation noise is ~1.5e-6."""
+    monkeypatch.setenv("WB_GEMM_FORCE", "1")
     xb = O.clustered_unit(n, d, 64, 1) if clustered else O.unit_gaussian(n, d, 100)
     xq = O.clustered_unit(nq, d, 64, 2) if clustered else O.unit_gaussian(nq, d, 200)
     ids = np.arange(n, dtype=np.int64) * 3 + 1
@@ -253,11 +254,28 @@ def test_gemm_path_matches_oracle(faiss, n, d, nq, k, clustered):
     Dr, Ir = O.flat_search(xb, xq, k, ids)
     O.compare_topk(D, I, Dr, Ir, band=4e-6)
     # the CUDA-core path on the same index gives the same members (different kernel, same contract)
-    D8, I8 = idx.search(xq[:8], k)
-    O.compare_topk(D8, I8, Dr[:8], Ir[:8])
+    D8, I8 = idx.search(xq[:4], k)
+    O.compare_topk(D8, I8, Dr[:4], Ir[:4])
 
 
-def test_gemm_path_duplicates_tie_rule(faiss):
+def test_kernel_choice_by_store_size(faiss):
+    """Dispatch heuristic: 16 queries over a 200 MB store stay on the CUDA-core scan (K2's fixed cost would
+    dominate); 256 queries over the same store go to the tensor cores.  Same results either way."""
+    n, d, k = 100000, 512, 10
+    xb = O.unit_gaussian(n, d, 3)
+    xq = O.unit_gaussian(256, d, 4)
+    idx = _flat(faiss, xb)
+    Dr, Ir = O.flat_search(xb, xq, k)
+    D, I = idx.search(xq[:16], k)
+    assert _gemm_stats(idx)[0] == 0
+    O.compare_topk(D, I, Dr[:16], Ir[:16])
+    D, I = idx.search(xq, k)
+    assert _gemm_stats(idx)[0] > 0
+    O.compare_topk(D, I, Dr, Ir, band=4e-6)
+
+
+def test_gemm_path_duplicates_tie_rule(faiss, monkeypatch):
+    monkeypatch.setenv("WB_GEMM_FORCE", "1")
     n, d, k = 60000, 256, 20
     xb = O.unit_gaussian(n, d, 5)
     xb[30000:30500] = xb[:500]
@@ -270,9 +288,10 @@ def test_gemm_path_duplicates_tie_rule(faiss):
         assert I[28 + j, 0] == 100 + j and I[28 + j, 1] == 30100 + j and D[28 + j, 0] == D[28 + j, 1]
 
 
-def test_gemm_overflow_falls_back_exactly(faiss):
+def test_gemm_overflow_falls_back_exactly(faiss, monkeypatch):
     """Adversarial order: rows sorted by ascending score for every query, so every row beats the running
     threshold and the candidate lists overflow; the batch is then repaired by the CUDA-core scan."""
+    monkeypatch.setenv("WB_GEMM_FORCE", "1")
     n, d, k = 120000, 64, 10
     rng = np.random.default_rng(0)
     base = O.unit_gaussian(1, d, 1)[0]
