@@ -5,7 +5,7 @@ import torch
 from wise_b200 import faiss_compat as faiss, _capi
 L = _capi.lib()
 nq = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-n, d = 2_000_000, 768
+n, d = (int(sys.argv[2]) if len(sys.argv) > 2 else 2_000_000), 768
 gen = torch.Generator(device="cuda"); gen.manual_seed(1)
 x = torch.randn(n, d, device="cuda", generator=gen); x /= x.norm(dim=1, keepdim=True)
 idx = faiss.IndexFlatIP(d); idx.reserve(n)

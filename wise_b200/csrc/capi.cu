@@ -537,7 +537,6 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     g.nq = (int)nq;
     g.nqb = nqb;
     g.bimg = h->gimg.as<float>();
-    g.debug_terms = env_int("WB_GEMM_DEBUG_TERMS", 3);
     g.thr = thr;
     g.keys = keys;
     g.cnt = cnt;
@@ -667,7 +666,6 @@ static int run_assign_gemm(wb_index* h, const float* x_ld, int64_t n, int32_t* a
     g.nq = (int)h->nlist;
     g.nqb = nqb;
     g.bimg = h->gimg.as<float>();
-    g.debug_terms = 3;
     g.assign_out = assign_out;
     g.best_out = best_out;
     const int64_t ntiles = (n + kGemmBM - 1) / kGemmBM;

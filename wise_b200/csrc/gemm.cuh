@@ -49,12 +49,15 @@ template <int BN>
 struct GemmCfg {
     static constexpr int kBBytes = 2 * BN * kGemmBK * 4;             // hi image + lo image of one k-chunk
     static constexpr int kTmemAOff = 2 * BN;                          // TMEM: D0 | D1 | A ring (64 columns per slot)
-    // Ring 2 ("operand slots"): query image in shared memory + split A operand in TMEM; freed by tcgen05.commit.
+    // Ring 2 ("operand slots"): query image chunk in shared memory + split A operand in TMEM.  ONE barrier per slot
+    // collects the 4 transform-warp arrivals and the image copy's transaction bytes, so the MMA thread - a serial
+    // instruction stream that is on the critical path at small BN - waits once per chunk; freed by tcgen05.commit.
+    // (A deeper, separate image ring was measured and did not help: the refill latency is not the limiter.)
     static constexpr int kSlots = (kTmemCols - kTmemAOff) / 64;       // 4 / 6 / 7 for BN = 128 / 64 / 32
     // Ring 1: raw fp32 row tiles straight from TMA; freed by the transform warps, so it can run far ahead of
     // the MMAs - it is what keeps enough bytes in flight to cover the loaded HBM latency (~3.5 us).
     static constexpr int kRawStages = (224 * 1024 - kSlots * kBBytes) / kGemmABytes;
-    static constexpr int kNumBars = 2 * kRawStages + 3 * kSlots + 4;
+    static constexpr int kNumBars = 2 * kRawStages + 2 * kSlots + 4;
     static constexpr size_t kSmemBytes =
         1024 + (size_t)kRawStages * kGemmABytes + (size_t)kSlots * kBBytes + kNumBars * 8 + 16 + 2 * BN * 4;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -65,7 +68,6 @@ struct GemmParams {
     int nchunks;                  // ceil(ld / 32)
     int nq;                       // real queries
     int nqb;                      // query blocks of BN queries
-    int debug_terms;              // timing experiments only: number of split terms issued (3 = correct)
     // ARGMAX mode (K4 add-time assignment, K6 k-means assignment): rows = points, queries = centroids;
     // each row keeps a running (max score, lowest index) over all query blocks - no candidate lists.
     int32_t* assign_out;          // [rows] argmax query index
@@ -113,6 +115,14 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+// 64-bit descriptor from its two words.  Only the start-address field (low 14 bits of the low word) changes between
+// MMAs, so the issuing thread adds byte offsets >> 4 to the low word with 32-bit adds and never builds carries.
+__device__ __forceinline__ uint64_t desc_from_words(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
 }
 
 // cute::UMMA::InstrDescriptor: c=F32 [4,6) | a=TF32 [7,10) | b=TF32 [10,13) | K-major A,B | N>>3 [17,23) | M>>4 [24,29)
@@ -205,8 +215,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
     unsigned char* bimg_s = raw + (size_t)kRaw * kGemmABytes;
     uint64_t* raw_full = reinterpret_cast<uint64_t*>(bimg_s + (size_t)kSlots * kBBytes);
     uint64_t* raw_empty = raw_full + kRaw;
-    uint64_t* b_full = raw_empty + kRaw;
-    uint64_t* a_full = b_full + kSlots;
+    uint64_t* a_full = raw_empty + kRaw;  // slot operands ready: A in TMEM (4 warp arrivals) + image bytes (1 + tx)
     uint64_t* slot_empty = a_full + kSlots;
     uint64_t* d_full = slot_empty + kSlots;
     uint64_t* d_empty = d_full + 2;
@@ -240,8 +249,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             mbar_init(&raw_empty[s], 4);  // 4 transform warps
         }
         for (int s = 0; s < kSlots; ++s) {
-            mbar_init(&b_full[s], 1);
-            mbar_init(&a_full[s], 4);      // 4 transform warps
+            mbar_init(&a_full[s], 5);      // 4 transform warps + producer B's arrive.expect_tx
             mbar_init(&slot_empty[s], 1);  // tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
@@ -295,8 +303,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                 for (int c = 0; c < p.nchunks; ++c) {
                     mbar_wait(&slot_empty[s], ph ^ 1u);
                     if (elect_one_sync()) {
-                        mbar_arrive_expect_tx(&b_full[s], kBBytes);
-                        bulk_g2s(bimg_s + (size_t)s * kBBytes, bsrc + (size_t)c * (kBBytes / 4), kBBytes, &b_full[s]);
+                        mbar_arrive_expect_tx(&a_full[s], kBBytes);
+                        bulk_g2s(bimg_s + (size_t)s * kBBytes, bsrc + (size_t)c * (kBBytes / 4), kBBytes, &a_full[s]);
                     }
                     __syncwarp();
                     if (++s == kSlots) { s = 0; ph ^= 1u; }
@@ -307,7 +315,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         // =============================== MMA issuer =============================================
         {   // converged warp; the elected lane issues the MMAs and the commits that track them
             constexpr uint32_t idesc = umma_idesc_tf32(kGemmBM, BN);
-            const uint64_t desc_hi0 = umma_smem_desc(smem_u32(bimg_s), BN * 16, 128);  // slot 0, k-step 0
+            const uint64_t desc0 = umma_smem_desc(smem_u32(bimg_s), BN * 16, 128);  // stage 0, k-step 0
+            const uint32_t desc_lo0 = (uint32_t)desc0, desc_w1 = (uint32_t)(desc0 >> 32);
             int s = 0;
             uint32_t ph = 0;
             int buf = 0;
@@ -317,23 +326,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
                 for (int c = 0; c < p.nchunks; ++c) {
-                    mbar_wait(&b_full[s], ph);  // query image landed
-                    mbar_wait(&a_full[s], ph);  // A hi/lo written to TMEM
+                    mbar_wait(&a_full[s], ph);  // A hi/lo written to TMEM and the query image landed
                     tc_fence_after();
                     if (elect_one_sync()) {
+                        // The issuing thread is a serial instruction stream (~4-5 cycles per dependent uniform
+                        // instruction): every instruction here is on the kernel's critical path at small BN
+                        // (measured: 455 of 735 cycles per chunk, profiles/r01/gemm_experiments.md).
                         const uint32_t a_hi = tmem_base + (uint32_t)(kTmemAOff + s * 64);
                         const uint32_t a_lo = a_hi + 32;
-                        // descriptors differ only in the start-address field: add (bytes >> 4) to the low word
-                        const uint64_t dh0 = desc_hi0 + (uint64_t)(((uint32_t)s * kBBytes) >> 4);
-                        const uint64_t dl0 = dh0 + (uint64_t)((kBBytes / 2) >> 4);
+                        const uint32_t dh0 = desc_lo0 + (uint32_t)s * (uint32_t)(kBBytes >> 4);
 #pragma unroll
                         for (int j = 0; j < kGemmBK / 8; ++j) {
                             // one k-step = 8 tf32 = two 16-byte k columns: LBO = BN*16 B, SBO = 128 B
-                            const uint64_t dh = dh0 + (uint64_t)((j * 2 * BN * 16) >> 4);
-                            const uint64_t dl = dl0 + (uint64_t)((j * 2 * BN * 16) >> 4);
+                            const uint64_t dh = desc_from_words(dh0 + (uint32_t)((j * 2 * BN * 16) >> 4), desc_w1);
+                            const uint64_t dl =
+                                desc_from_words(dh0 + (uint32_t)((kBBytes / 2 + j * 2 * BN * 16) >> 4), desc_w1);
                             umma_tf32_ts(d_tmem, a_hi + j * 8, dh, idesc, (c | j) != 0);
-                            if (p.debug_terms > 1) umma_tf32_ts(d_tmem, a_hi + j * 8, dl, idesc, 1);
-                            if (p.debug_terms > 2) umma_tf32_ts(d_tmem, a_lo + j * 8, dh, idesc, 1);
+                            umma_tf32_ts(d_tmem, a_hi + j * 8, dl, idesc, 1);
+                            umma_tf32_ts(d_tmem, a_lo + j * 8, dh, idesc, 1);
                         }
                         umma_commit(&slot_empty[s]);  // slot (smem image + TMEM A) is free once these MMAs retire
                         if (c == p.nchunks - 1) umma_commit(&d_full[buf]);
@@ -351,14 +361,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         const int set = warp >= 12 ? 1 : 0;
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
-        int64_t g = 0;                      // running chunk number over all work items of this CTA
+        // ring positions of the running chunk (advanced for every chunk, whichever set handles it)
+        int sr = 0, ss = 0, par = 0;
+        uint32_t phr = 0, phs = 0;
+        auto next_chunk = [&]() {
+            if (++sr == kRaw) { sr = 0; phr ^= 1u; }
+            if (++ss == kSlots) { ss = 0; phs ^= 1u; }
+            par ^= 1;
+        };
         for (int64_t it = 0; it < my_work; ++it) {
-            for (int c = 0; c < p.nchunks; ++c, ++g) {
-                if ((g & 1) != set) continue;
-                const int sr = (int)(g % kRaw);
-                const uint32_t phr = (uint32_t)((g / kRaw) & 1);
-                const int ss = (int)(g % kSlots);
-                const uint32_t phs = (uint32_t)((g / kSlots) & 1);
+            for (int c = 0; c < p.nchunks; ++c, next_chunk()) {
+                if (par != set) continue;
                 mbar_wait(&raw_full[sr], phr);
                 const unsigned char* a_raw = raw + (size_t)sr * kGemmABytes + (size_t)r * 128;
                 uint32_t hi[32], lo[32];
