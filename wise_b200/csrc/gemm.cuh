@@ -45,6 +45,9 @@ constexpr int kBarEpilogue = 2;
 
 // Per query-block width BN (UMMA N = 32 / 64 / 128): small batches use a narrow block so the kernel
 // stays bound by the HBM stream of the rows instead of by padded MMAs and query-image traffic.
+#ifndef WB_GEMM_SLOTS
+#define WB_GEMM_SLOTS(BN) 7  // experiment knob: same-box A/B of 7/6, 6/5 and 5/4 slots (BN 32/64) showed no difference
+#endif
 template <int BN>
 struct GemmCfg {
     static constexpr int kBBytes = 2 * BN * kGemmBK * 4;             // hi image + lo image of one k-chunk
@@ -53,7 +56,9 @@ struct GemmCfg {
     // collects the 4 transform-warp arrivals and the image copy's transaction bytes, so the MMA thread - a serial
     // instruction stream that is on the critical path at small BN - waits once per chunk; freed by tcgen05.commit.
     // (A deeper, separate image ring was measured and did not help: the refill latency is not the limiter.)
-    static constexpr int kSlots = (kTmemCols - kTmemAOff) / 64;       // 4 / 6 / 7 for BN = 128 / 64 / 32
+    // The slot count is not critical (measured: 5 slots + 11 raw stages == 7 slots + 10 raw stages at BN = 32).
+    static constexpr int kSlotsTmem = (kTmemCols - kTmemAOff) / 64;  // 4 / 6 / 7 for BN = 128 / 64 / 32
+    static constexpr int kSlots = kSlotsTmem < WB_GEMM_SLOTS(BN) ? kSlotsTmem : WB_GEMM_SLOTS(BN);
     // Ring 1: raw fp32 row tiles straight from TMA; freed by the transform warps, so it can run far ahead of
     // the MMAs - it is what keeps enough bytes in flight to cover the loaded HBM latency (~3.5 us).
     static constexpr int kRawStages = (224 * 1024 - kSlots * kBBytes) / kGemmABytes;
