@@ -14,6 +14,12 @@ L.wb_set_timing(idx._h, 1)
 st = torch.cuda.current_stream().cuda_stream
 q = torch.randn(nq, d, device="cuda"); q /= q.norm(dim=1, keepdim=True)
 D = torch.empty(nq, 100, device="cuda"); I = torch.empty(nq, 100, dtype=torch.int64, device="cuda")
-for _ in range(3):
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+ts = []
+for _ in range(iters):
     _capi.check(L.wb_search_dev(idx._h, nq, q.data_ptr(), 100, 1, D.data_ptr(), I.data_ptr(), st)); torch.cuda.synchronize()
-    print(nq, L.wb_last_scan_ms(idx._h), flush=True)
+    ts.append(L.wb_last_scan_ms(idx._h))
+    if iters <= 3: print(nq, ts[-1], flush=True)
+if iters > 3:
+    tail = sorted(ts[iters // 2:])
+    print(nq, "min %.3f  median(last half) %.3f ms over %d searches" % (min(ts), tail[len(tail) // 2], iters), flush=True)

@@ -472,7 +472,8 @@ static bool gemm_eligible(const wb_index* h, int64_t nrows, int64_t nq, int k, i
 template <int BN>
 static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const float* q_ld, int64_t nq, int k, int cap,
                          const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed, bool* overflowed) {
-    using Cfg = GemmCfg<BN>;
+    constexpr bool kFold = kGemmFold<BN, false>;
+    using Cfg = GemmCfg<BN, kFold>;
     constexpr int kGemmBN = BN;
     constexpr int kGemmBBytes = Cfg::kBBytes;
     constexpr size_t kGemmSmemBytes = Cfg::kSmemBytes;
@@ -501,8 +502,8 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
             split_queries_kernel<BN / 2><<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, 2 * nqb,
                                                                                   h->gimg.as<float>());
         } else {
-            split_queries_kernel<BN><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb,
-                                                                              h->gimg.as<float>());
+            split_queries_kernel<BN, kFold><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb,
+                                                                                     h->gimg.as<float>());
         }
         CK(cudaGetLastError());
         h->launches += 2;

@@ -48,10 +48,18 @@ constexpr int kBarEpilogue = 2;
 #ifndef WB_GEMM_SLOTS
 #define WB_GEMM_SLOTS(BN) 7  // experiment knob: same-box A/B of 7/6, 6/5 and 5/4 slots (BN 32/64) showed no difference
 #endif
-template <int BN>
+// FOLD (search mode, BN <= 64): every tcgen05.mma costs the tensor pipe ~45 cycles however small N is (measured:
+// 12 MMAs of N = 32 per chunk = 540 cycles > the 508 cycles HBM allows a chunk at 1.55 GHz), so the three split
+// terms are issued as TWO instructions per k-step: A_hi x [Q_hi ; Q_lo] (N = 2*BN, the lo image stacked under the hi
+// image as extra operand rows) and A_lo x Q_hi (N = BN, the first rows of the same descriptor).  The accumulator
+// tile is then 2*BN columns wide - [hi.hi + lo.hi | hi.lo] - and the epilogue adds the two halves.
+template <int BN, bool ARGMAX>
+constexpr bool kGemmFold = !ARGMAX && BN <= 64;
+template <int BN, bool FOLD = false>
 struct GemmCfg {
     static constexpr int kBBytes = 2 * BN * kGemmBK * 4;             // hi image + lo image of one k-chunk
-    static constexpr int kTmemAOff = 2 * BN;                          // TMEM: D0 | D1 | A ring (64 columns per slot)
+    static constexpr int kDCols = FOLD ? 2 * BN : BN;                 // accumulator columns per buffer
+    static constexpr int kTmemAOff = 2 * kDCols;                      // TMEM: D0 | D1 | A ring (64 columns per slot)
     // Ring 2 ("operand slots"): query image chunk in shared memory + split A operand in TMEM.  ONE barrier per slot
     // collects the 4 transform-warp arrivals and the image copy's transaction bytes, so the MMA thread - a serial
     // instruction stream that is on the critical path at small BN - waits once per chunk; freed by tcgen05.commit.
@@ -165,7 +173,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // ---- query pre-split: fp32 queries -> (hi, lo) images in the UMMA no-swizzle K-major layout ----
 // image[qb][chunk][half][k16 = 0..7][n = 0..BN-1][4 floats]: a core matrix (8 queries x 16 B) is 128
 // contiguous bytes, SBO = 128 B between 8-query groups, LBO = BN*16 B between 16-byte k columns.
-template <int BN>
+// FOLD: image[qb][chunk][k16][half][n][4] - one operand of 2*BN rows (hi rows, then lo rows), LBO = 2*BN*16 B.
+template <int BN, bool FOLD = false>
 __global__ void split_queries_kernel(const float* q, int nq, int ld, int nchunks, int nqb, float* img) {
     constexpr int kGemmBN = BN;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one float4 per thread
@@ -190,9 +199,10 @@ __global__ void split_queries_kernel(const float* q, int nq, int ld, int nchunks
         lo[e] = v[e] - hi[e];
     }
     const size_t base = ((size_t)(qb * nchunks + chunk) * 2) * (8 * kGemmBN * 4);
-    const size_t off = ((size_t)k16 * kGemmBN + n) * 4;
+    const size_t off = FOLD ? ((size_t)k16 * 2 * kGemmBN + n) * 4 : ((size_t)k16 * kGemmBN + n) * 4;
+    const size_t lo_off = FOLD ? (size_t)kGemmBN * 4 : (size_t)8 * kGemmBN * 4;
     *reinterpret_cast<float4*>(img + base + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<float4*>(img + base + 8 * kGemmBN * 4 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<float4*>(img + base + lo_off + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 __global__ void init_gemm_state_kernel(float* thr, int nq, int nq_pad, int* cnt, uint64_t* keys, int k, int kstride,
@@ -208,7 +218,9 @@ __global__ void init_gemm_state_kernel(float* thr, int nq, int nq_pad, int* cnt,
 template <int BN, bool ARGMAX>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    constexpr bool FOLD = kGemmFold<BN, ARGMAX>;
+    using Cfg = GemmCfg<BN, FOLD>;
+    constexpr int kDCols = Cfg::kDCols;
     constexpr int kRaw = Cfg::kRawStages;
     constexpr int kSlots = Cfg::kSlots;
     constexpr int kBBytes = Cfg::kBBytes;
@@ -320,7 +332,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         // =============================== MMA issuer =============================================
         {   // converged warp; the elected lane issues the MMAs and the commits that track them
             constexpr uint32_t idesc = umma_idesc_tf32(kGemmBM, BN);
-            const uint64_t desc0 = umma_smem_desc(smem_u32(bimg_s), BN * 16, 128);  // stage 0, k-step 0
+            constexpr uint32_t idesc_fold = umma_idesc_tf32(kGemmBM, 2 * BN);
+            constexpr int kLbo = (FOLD ? 2 * BN : BN) * 16;  // bytes between 16-byte k columns of the image
+            const uint64_t desc0 = umma_smem_desc(smem_u32(bimg_s), kLbo, 128);  // stage 0, k-step 0
             const uint32_t desc_lo0 = (uint32_t)desc0, desc_w1 = (uint32_t)(desc0 >> 32);
             int s = 0;
             uint32_t ph = 0;
@@ -329,7 +343,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             for (int64_t it = 0; it < my_work; ++it) {
                 mbar_wait(&d_empty[buf], dph ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kDCols);
                 for (int c = 0; c < p.nchunks; ++c) {
                     mbar_wait(&a_full[s], ph);  // A hi/lo written to TMEM and the query image landed
                     tc_fence_after();
@@ -342,13 +356,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                         const uint32_t dh0 = desc_lo0 + (uint32_t)s * (uint32_t)(kBBytes >> 4);
 #pragma unroll
                         for (int j = 0; j < kGemmBK / 8; ++j) {
-                            // one k-step = 8 tf32 = two 16-byte k columns: LBO = BN*16 B, SBO = 128 B
-                            const uint64_t dh = desc_from_words(dh0 + (uint32_t)((j * 2 * BN * 16) >> 4), desc_w1);
-                            const uint64_t dl =
-                                desc_from_words(dh0 + (uint32_t)((kBBytes / 2 + j * 2 * BN * 16) >> 4), desc_w1);
-                            umma_tf32_ts(d_tmem, a_hi + j * 8, dh, idesc, (c | j) != 0);
-                            umma_tf32_ts(d_tmem, a_hi + j * 8, dl, idesc, 1);
-                            umma_tf32_ts(d_tmem, a_lo + j * 8, dh, idesc, 1);
+                            // one k-step = 8 tf32 = two 16-byte k columns: LBO = kLbo, SBO = 128 B
+                            const uint64_t dh = desc_from_words(dh0 + (uint32_t)((j * 2 * kLbo) >> 4), desc_w1);
+                            if constexpr (FOLD) {
+                                umma_tf32_ts(d_tmem, a_hi + j * 8, dh, idesc_fold, (c | j) != 0);  // [hi.hi | hi.lo]
+                                umma_tf32_ts(d_tmem, a_lo + j * 8, dh, idesc, 1);                  // lo.hi -> first half
+                            } else {
+                                const uint64_t dl =
+                                    desc_from_words(dh0 + (uint32_t)((kBBytes / 2 + j * 2 * kLbo) >> 4), desc_w1);
+                                umma_tf32_ts(d_tmem, a_hi + j * 8, dh, idesc, (c | j) != 0);
+                                umma_tf32_ts(d_tmem, a_hi + j * 8, dl, idesc, 1);
+                                umma_tf32_ts(d_tmem, a_lo + j * 8, dh, idesc, 1);
+                            }
                         }
                         umma_commit(&slot_empty[s]);  // slot (smem image + TMEM A) is free once these MMAs retire
                         if (c == p.nchunks - 1) umma_commit(&d_full[buf]);
@@ -431,11 +450,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             }
             mbar_wait(&d_full[buf], dph);
             tc_fence_after();
-            const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
+            const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kDCols);
 #pragma unroll 1
             for (int cb = 0; cb < BN / 32; ++cb) {
                 uint32_t v[32];
                 tmem_ld32(td + cb * 32, v);
+                if constexpr (FOLD) {
+                    uint32_t w[32];
+                    tmem_ld32(td + BN + cb * 32, w);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if constexpr (ARGMAX) {
                     const int q0 = qb * BN + cb * 32;
