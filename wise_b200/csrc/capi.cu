@@ -497,11 +497,14 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
                                                                             kstride, overflow);
         CK(cudaGetLastError());
         const int64_t n2 = (int64_t)nqb * nchunks * 8 * kGemmBN;
-        if (use2) {  // the 2-CTA kernel wants one image per 64 queries (each CTA of a pair holds half a block)
-            const int64_t n3 = (int64_t)(2 * nqb) * nchunks * 8 * (BN / 2);
-            split_queries_kernel<BN / 2><<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, 2 * nqb,
-                                                                                  h->gimg.as<float>());
-        } else {
+        if constexpr (BN >= 128) {
+            if (use2) {  // the 2-CTA kernel wants one image per 64 queries (each CTA of a pair holds half a block)
+                const int64_t n3 = (int64_t)(2 * nqb) * nchunks * 8 * (BN / 2);
+                split_queries_kernel<BN / 2><<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks,
+                                                                                      2 * nqb, h->gimg.as<float>());
+            }
+        }
+        if (!use2) {
             split_queries_kernel<BN, kFold><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb,
                                                                                      h->gimg.as<float>());
         }
@@ -573,19 +576,20 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
         g.row_end = r1;
         const int64_t nwork = ((r1 - r0 + kGemmBM - 1) / kGemmBM) * nqb;
         const unsigned grid = (unsigned)std::min<int64_t>(nwork, h->sm_count);
-        if (use2) {
-            static thread_local bool a2[64] = {};
-            if (dev >= 64 || !a2[dev]) {
-                CK(cudaFuncSetAttribute(gemm2_topk_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)Gemm2Cfg<BN>::kSmemBytes));
-                if (dev < 64) a2[dev] = true;
+        if constexpr (BN >= 128) {  // the CTA pair exists for 128-query blocks only
+            if (use2) {
+                static thread_local bool a2[64] = {};
+                if (dev >= 64 || !a2[dev]) {
+                    CK(cudaFuncSetAttribute(gemm2_topk_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)Gemm2Cfg<BN>::kSmemBytes));
+                    if (dev < 64) a2[dev] = true;
+                }
+                const int64_t ntp = ((r1 - r0 + kGemmBM - 1) / kGemmBM + 1) / 2;
+                const unsigned grid2 = 2u * (unsigned)std::min<int64_t>(ntp * nqb, h->sm_count / 2);
+                gemm2_topk_kernel<BN, false><<<grid2, kGemmThreads, Gemm2Cfg<BN>::kSmemBytes, st>>>(tmap, g);
             }
-            const int64_t ntp = ((r1 - r0 + kGemmBM - 1) / kGemmBM + 1) / 2;
-            const unsigned grid2 = 2u * (unsigned)std::min<int64_t>(ntp * nqb, h->sm_count / 2);
-            gemm2_topk_kernel<BN, false><<<grid2, kGemmThreads, Gemm2Cfg<BN>::kSmemBytes, st>>>(tmap, g);
-        } else {
-            gemm_topk_kernel<BN, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
         }
+        if (!use2) gemm_topk_kernel<BN, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
         CK(cudaGetLastError());
         const bool last = r1 >= nrows;
         c.D = last ? D : nullptr;
@@ -610,6 +614,10 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
 static int run_flat_gemm(wb_index* h, const float* rows, int64_t nrows, const float* q_ld, int64_t nq, int k, int cap,
                          const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed, bool* overflowed) {
     const int bn_max = env_int("WB_GEMM_BN", 128);
+    // 16-query blocks halve the image traffic and the MMA work of a half-empty 32-query block (K2 is power-capped at
+    // small batches: 992 W and 1.37 GHz at batch 16)
+    if (nq <= 16 && bn_max >= 16 && env_int("WB_GEMM_BN16", 1))
+        return run_flat_gemm_t<16>(h, rows, nrows, q_ld, nq, k, cap, ids, D, I, st, timed, overflowed);
     if (nq <= 32 && bn_max >= 32) return run_flat_gemm_t<32>(h, rows, nrows, q_ld, nq, k, cap, ids, D, I, st, timed, overflowed);
     if ((nq <= 64 && bn_max >= 64) || bn_max < 128)
         return run_flat_gemm_t<64>(h, rows, nrows, q_ld, nq, k, cap, ids, D, I, st, timed, overflowed);

@@ -451,18 +451,25 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             mbar_wait(&d_full[buf], dph);
             tc_fence_after();
             const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kDCols);
+            constexpr int kEpi = BN < 32 ? BN : 32;  // query columns handled per TMEM load
 #pragma unroll 1
-            for (int cb = 0; cb < BN / 32; ++cb) {
+            for (int cb = 0; cb < BN / kEpi; ++cb) {
                 uint32_t v[32];
-                tmem_ld32(td + cb * 32, v);
-                if constexpr (FOLD) {
+                tmem_ld32(td + cb * 32, v);  // BN = 16 (always folded): both 16-column halves in one load
+                if constexpr (FOLD && BN >= 32) {
                     uint32_t w[32];
                     tmem_ld32(td + BN + cb * 32, w);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+                } else {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if constexpr (FOLD) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v[16 + j]));
+                    }
                 }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if constexpr (ARGMAX) {
                     const int q0 = qb * BN + cb * 32;
 #pragma unroll
@@ -477,12 +484,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < kEpi; ++j) {
                         const float sc = __uint_as_float(v[j]);
-                        const bool pass = row_ok && sc > thr_s[buf * BN + cb * 32 + j];
+                        const bool pass = row_ok && sc > thr_s[buf * BN + cb * kEpi + j];
                         const unsigned m = __ballot_sync(0xffffffffu, pass);
                         if (m) {
-                            const int qi = qb * BN + cb * 32 + j;  // < nq: padded queries have thr = +inf
+                            const int qi = qb * BN + cb * kEpi + j;  // < nq: padded queries have thr = +inf
                             int base = 0;
                             if (lane == (__ffs(m) - 1)) base = atomicAdd(&p.cnt[qi], __popc(m));
                             base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
