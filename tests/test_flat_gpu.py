@@ -258,6 +258,26 @@ def test_gemm_path_matches_oracle(faiss, monkeypatch, n, d, nq, k, clustered):
     O.compare_topk(D8, I8, Dr[:4], Ir[:4])
 
 
+@pytest.mark.parametrize("filt", ["0", "1"])
+def test_gemm_filter_and_refine_unnormalised(faiss, monkeypatch, filt):
+    """K2's later epochs issue only the hi x hi term and keep a row when its one-term score exceeds
+    thr - margin, margin = c * |q| * max|x|; candidates are re-scored exactly.  Rows and queries with very different
+    norms (0.25 .. 4) make a too-small margin lose true neighbours; WB_GEMM_FILTER=0 is the all-3xTF32 path."""
+    monkeypatch.setenv("WB_GEMM_FORCE", "1")
+    monkeypatch.setenv("WB_GEMM_FILTER", filt)
+    n, d, nq, k = 150000, 384, 48, 50
+    rng = np.random.default_rng(11)
+    xb = O.unit_gaussian(n, d, 21) * rng.uniform(0.25, 4.0, size=(n, 1)).astype(np.float32)
+    xq = O.unit_gaussian(nq, d, 22) * rng.uniform(0.5, 2.0, size=(nq, 1)).astype(np.float32)
+    idx = _flat(faiss, xb)
+    D, I = idx.search(xq, k)
+    epochs, fallbacks = _gemm_stats(idx)
+    assert epochs >= 3 and fallbacks == 0
+    Dr, Ir = O.flat_search(xb, xq, k)
+    scale = 4.0 * 2.0  # rounding errors scale with |q||x| (1 for the unit-norm features the tolerances are quoted for)
+    O.compare_topk(D, I, Dr, Ir, score_tol=1e-5 * scale, band=4e-6 * scale)
+
+
 def test_kernel_choice_by_store_size(faiss):
     """Dispatch heuristic: 16 queries over a 200 MB store stay on the CUDA-core scan (K2's fixed cost would
     dominate); 256 queries over the same store go to the tensor cores.  Same results either way."""

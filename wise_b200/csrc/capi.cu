@@ -88,6 +88,7 @@ struct wb_index {
     int64_t* ids = nullptr;
     int32_t* assign = nullptr;  // IVF: list of each row
     int64_t n = 0, cap = 0;
+    float* norm2_max = nullptr;  // device scalar: max |row|^2 over everything ever added (K2 filter margin)
     // IVF quantizer + CSR inverted lists (row indices grouped by list, insertion order kept)
     float* centroids = nullptr;  // [nlist, ld]
     uint32_t* perm = nullptr;
@@ -96,7 +97,7 @@ struct wb_index {
     bool csr_dirty = true;
     bool contiguous = false;  // rows physically grouped by list (perm is the identity and not stored)
     // scratch
-    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gkeys, gstate, eD, eI;
+    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gkeys, gstate, gmargin, eD, eI;
     int64_t gemm_launches = 0, gemm_fallbacks = 0;
     // device properties
     int sm_count = 148;
@@ -142,6 +143,8 @@ static int create_common(int d, int device, bool ivf, int64_t nlist, wb_index** 
         CK(cudaEventCreate(&h->ev0[i]));
         CK(cudaEventCreate(&h->ev1[i]));
     }
+    CK(cudaMalloc(&h->norm2_max, sizeof(float)));
+    CK(cudaMemsetAsync(h->norm2_max, 0, sizeof(float), h->stream));
     if (ivf) {
         CK(cudaMalloc(&h->centroids, (size_t)nlist * h->ld * sizeof(float)));
         CK(cudaMemsetAsync(h->centroids, 0, (size_t)nlist * h->ld * sizeof(float), h->stream));
@@ -166,10 +169,11 @@ extern "C" int wb_free(wb_index* h) {
     cudaFree(h->ids);
     cudaFree(h->assign);
     cudaFree(h->centroids);
+    cudaFree(h->norm2_max);
     cudaFree(h->perm);
     cudaFree(h->list_off);
     for (DevBuf* b : {&h->parts, &h->qbuf, &h->dbuf, &h->ibuf, &h->pD, &h->pI, &h->xbuf, &h->idbuf, &h->misc,
-                      &h->kperm, &h->koff, &h->gimg, &h->gkeys, &h->gstate, &h->eD, &h->eI})
+                      &h->kperm, &h->koff, &h->gimg, &h->gkeys, &h->gstate, &h->gmargin, &h->eD, &h->eI})
         b->release();
     for (int i = 0; i < wb_index::kEvRing; ++i) {
         cudaEventDestroy(h->ev0[i]);
@@ -472,6 +476,9 @@ static bool gemm_eligible(const wb_index* h, int64_t nrows, int64_t nq, int k, i
 template <int BN>
 static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const float* q_ld, int64_t nq, int k, int cap,
                          const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed, bool* overflowed) {
+    // Filter-and-refine (main row store only, whose norms are tracked): after the first epoch the GEMM issues only
+    // the hi x hi term and the compaction re-scores the few hundred candidates per query exactly in fp32.
+    const bool filter = rows == h->rows && env_int("WB_GEMM_FILTER", 1) != 0;
     constexpr bool kFold = kGemmFold<BN, false>;
     using Cfg = GemmCfg<BN, kFold>;
     constexpr int kGemmBN = BN;
@@ -488,6 +495,19 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     TRY(h->gkeys.ensure((size_t)nq * kstride * sizeof(uint64_t)));
     TRY(h->gstate.ensure((size_t)nqb * kGemmBN * 4 + (size_t)nq * 4 + 64));
     float* thr = h->gstate.as<float>();
+    float* margin = nullptr;
+    if (filter) {
+        TRY(h->gmargin.ensure((size_t)nqb * kGemmBN * 4));
+        margin = h->gmargin.as<float>();
+        // |exact - hi.hi| <= 2^-9 |x||q| (two truncations to tf32, Cauchy-Schwarz) + fp32 accumulation slack
+        // (n-term fp32 accumulation: <= n * 2^-23 * sum |x_i q_i| even if the tensor core truncates)
+        const float c_margin = 1.953125e-3f + (float)ld * 1.1920929e-7f * 1.1f + 1e-5f;
+        const int nqp = nqb * kGemmBN;
+        query_margin_kernel<<<(unsigned)((nqp * 32 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, nqp, ld, h->norm2_max,
+                                                                              c_margin, margin);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
     int* cnt = reinterpret_cast<int*>(thr + (size_t)nqb * kGemmBN);
     int* overflow = cnt + nq;
     uint64_t* keys = h->gkeys.as<uint64_t>();
@@ -529,6 +549,8 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     CK(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_done[dev]) {
         CK(cudaFuncSetAttribute(gemm_topk_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+        CK(cudaFuncSetAttribute(gemm_topk_kernel<BN, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)kGemmSmemBytes));
         if (dev < 64) attr_done[dev] = true;
     }
     TRY(merge_smem_optin<true>());
@@ -543,6 +565,7 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     g.nqb = nqb;
     g.bimg = h->gimg.as<float>();
     g.thr = thr;
+    g.margin = margin;
     g.keys = keys;
     g.cnt = cnt;
     g.overflow = overflow;
@@ -562,6 +585,9 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     c.cnt = cnt;
     c.thr = thr;
     c.ids = ids;
+    c.rows = rows;
+    c.q = q_ld;
+    c.ld = ld;
     // next epoch = growth x (rows seen so far): a query then collects ~k*ln(1+growth) survivors per epoch, far
     // below `cap`; fewer, larger epochs mean fewer launch gaps and compactions (each costs ~50 us)
     const double growth = std::min(12.0, std::max(0.25, (double)cap / (4.0 * k)));
@@ -576,24 +602,39 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
         g.row_end = r1;
         const int64_t nwork = ((r1 - r0 + kGemmBM - 1) / kGemmBM) * nqb;
         const unsigned grid = (unsigned)std::min<int64_t>(nwork, h->sm_count);
+        // first epoch: 3xTF32 scores select, the winners are re-scored; later epochs: one-term filter, candidates re-scored
+        const bool one_term = filter && r0 > 0;
+        c.rescore = filter ? (r0 == 0 ? 2 : 1) : 0;
         if constexpr (BN >= 128) {  // the CTA pair exists for 128-query blocks only
             if (use2) {
                 static thread_local bool a2[64] = {};
                 if (dev >= 64 || !a2[dev]) {
                     CK(cudaFuncSetAttribute(gemm2_topk_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)Gemm2Cfg<BN>::kSmemBytes));
+                    CK(cudaFuncSetAttribute(gemm2_topk_kernel<BN, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)Gemm2Cfg<BN>::kSmemBytes));
                     if (dev < 64) a2[dev] = true;
                 }
                 const int64_t ntp = ((r1 - r0 + kGemmBM - 1) / kGemmBM + 1) / 2;
                 const unsigned grid2 = 2u * (unsigned)std::min<int64_t>(ntp * nqb, h->sm_count / 2);
-                gemm2_topk_kernel<BN, false><<<grid2, kGemmThreads, Gemm2Cfg<BN>::kSmemBytes, st>>>(tmap, g);
+                if (one_term) gemm2_topk_kernel<BN, false, 1><<<grid2, kGemmThreads, Gemm2Cfg<BN>::kSmemBytes, st>>>(tmap, g);
+                else gemm2_topk_kernel<BN, false><<<grid2, kGemmThreads, Gemm2Cfg<BN>::kSmemBytes, st>>>(tmap, g);
             }
         }
-        if (!use2) gemm_topk_kernel<BN, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
+        if (!use2) {
+            if (one_term) gemm_topk_kernel<BN, false, 1><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
+            else gemm_topk_kernel<BN, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
+        }
         CK(cudaGetLastError());
         const bool last = r1 >= nrows;
         c.D = last ? D : nullptr;
         c.I = last ? I : nullptr;
+        if (c.rescore == 1) {
+            const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (int64_t)h->sm_count * 4 / nq));
+            rescore_candidates_kernel<<<dim3((unsigned)nq, gy), 256, 0, st>>>(c);
+            CK(cudaGetLastError());
+            h->launches++;
+        }
         compact_topk_kernel<<<(unsigned)nq, kMergeThreads, (size_t)c.S * 8, st>>>(c);
         CK(cudaGetLastError());
         h->launches += 2;
@@ -834,6 +875,12 @@ static int add_common(wb_index* h, int64_t n, const float* x, const int64_t* ids
         }
         const int64_t tot = n * h->ld;
         pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(src, dst, n, h->d, h->ld);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    {   // running max of |row|^2: the K2 filter epochs derive their safety margin from it
+        const unsigned blocks = (unsigned)std::min<int64_t>((n + 7) / 8, (int64_t)h->sm_count * 8);
+        row_norm2_max_kernel<<<blocks, 256, 0, st>>>(dst, n, h->ld, h->norm2_max);
         CK(cudaGetLastError());
         h->launches++;
     }

@@ -87,6 +87,7 @@ struct GemmParams {
     float* best_out;              // [rows] its score
     const float* bimg;            // [nqb][nchunks][2][8][BN][4] pre-split query images
     const float* thr;             // [nqb*BN] current k-th best score per query (+inf for padding)
+    const float* margin;          // [nqb*BN] TERMS == 1 only: bound on |exact - one-term score| per query
     uint64_t* keys;               // [nq][kstride]: [0,k) current top-k, [k, k+cap) candidates
     int* cnt;                     // [nq] candidates appended so far
     int* overflow;                // set when a candidate list ran out of room
@@ -215,9 +216,14 @@ __global__ void init_gemm_state_kernel(float* thr, int nq, int nq_pad, int* cnt,
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int BN, bool ARGMAX>
+// TERMS = 3: scores are the 3xTF32 sums (exact to ~1e-6).  TERMS = 1 ("filter" epochs of a search): only hi x hi is
+// issued - a third of the tensor work, no lo halves in TMEM - and a row becomes a candidate when its one-term score
+// exceeds thr - margin, margin >= |exact - one-term| (2^-9 |x||q| by Cauchy-Schwarz on the two truncations, plus
+// accumulation slack); compact_topk_kernel then re-scores the candidates in fp32, so the result is the exact top-k.
+template <int BN, bool ARGMAX, int TERMS = 3>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
+    static_assert(TERMS == 3 || (TERMS == 1 && !ARGMAX), "one-term scores are only a filter");
     constexpr bool FOLD = kGemmFold<BN, ARGMAX>;
     using Cfg = GemmCfg<BN, FOLD>;
     constexpr int kDCols = Cfg::kDCols;
@@ -358,7 +364,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                         for (int j = 0; j < kGemmBK / 8; ++j) {
                             // one k-step = 8 tf32 = two 16-byte k columns: LBO = kLbo, SBO = 128 B
                             const uint64_t dh = desc_from_words(dh0 + (uint32_t)((j * 2 * kLbo) >> 4), desc_w1);
-                            if constexpr (FOLD) {
+                            if constexpr (TERMS == 1) {
+                                umma_tf32_ts(d_tmem, a_hi + j * 8, dh, idesc, (c | j) != 0);  // hi.hi only (hi rows of the image)
+                            } else if constexpr (FOLD) {
                                 umma_tf32_ts(d_tmem, a_hi + j * 8, dh, idesc_fold, (c | j) != 0);  // [hi.hi | hi.lo]
                                 umma_tf32_ts(d_tmem, a_lo + j * 8, dh, idesc, 1);                  // lo.hi -> first half
                             } else {
@@ -407,7 +415,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                     for (int e = 0; e < 4; ++e) {
                         const uint32_t h = __float_as_uint(x[e]) & 0xFFFFE000u;
                         hi[ch * 4 + e] = h;
-                        lo[ch * 4 + e] = __float_as_uint(x[e] - __uint_as_float(h));
+                        if constexpr (TERMS != 1) lo[ch * 4 + e] = __float_as_uint(x[e] - __uint_as_float(h));
                     }
                 }
                 // NOTE: the raw stage is handed back only AFTER the TMEM store below.  Releasing it here
@@ -417,7 +425,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                 tc_fence_after();
                 const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kTmemAOff + ss * 64);
                 tmem_st32(ta, hi);
-                tmem_st32(ta + 32, lo);
+                if constexpr (TERMS != 1) tmem_st32(ta + 32, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
@@ -442,7 +450,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             const int64_t row = p.row_begin + tile * kGemmBM + quarter * 32 + lane;
             const bool row_ok = row < p.row_end;
             if constexpr (!ARGMAX) {
-                if (etid < BN) thr_s[buf * BN + etid] = p.thr[qb * BN + etid];
+                if (etid < BN) {
+                    float t = p.thr[qb * BN + etid];
+                    if constexpr (TERMS == 1) t -= p.margin[qb * BN + etid];  // -inf / +inf (padding) stay put
+                    thr_s[buf * BN + etid] = t;
+                }
                 named_bar_sync(kBarEpilogue, 128);
             } else if (qb == 0) {
                 best = -INFINITY;
@@ -456,7 +468,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             for (int cb = 0; cb < BN / kEpi; ++cb) {
                 uint32_t v[32];
                 tmem_ld32(td + cb * 32, v);  // BN = 16 (always folded): both 16-column halves in one load
-                if constexpr (FOLD && BN >= 32) {
+                if constexpr (FOLD && BN >= 32 && TERMS == 3) {
                     uint32_t w[32];
                     tmem_ld32(td + BN + cb * 32, w);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -464,7 +476,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
                 } else {
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if constexpr (FOLD) {
+                    if constexpr (FOLD && TERMS == 3) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v[16 + j]));
@@ -588,9 +600,10 @@ __device__ __forceinline__ void umma_tf32_ts_2cta(uint32_t d_tmem, uint32_t a_tm
         : "memory");
 }
 
-template <int BN, bool ARGMAX>
+template <int BN, bool ARGMAX, int TERMS = 3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
+    static_assert(TERMS == 3 || (TERMS == 1 && !ARGMAX), "one-term scores are only a filter");
     using Cfg2 = Gemm2Cfg<BN>;
     constexpr int kG2Half = Cfg2::kHalf;
     constexpr int kRaw = Cfg2::kRaw;
@@ -745,8 +758,10 @@ gemm2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) 
                         const uint64_t dh = dh0 + (uint64_t)((j * 2 * kG2Half * 16) >> 4);
                         const uint64_t dl = dl0 + (uint64_t)((j * 2 * kG2Half * 16) >> 4);
                         umma_tf32_ts_2cta(d_tmem, a_hi + j * 8, dh, idesc, (c | j) != 0);
-                        umma_tf32_ts_2cta(d_tmem, a_hi + j * 8, dl, idesc, 1);
-                        umma_tf32_ts_2cta(d_tmem, a_lo + j * 8, dh, idesc, 1);
+                        if constexpr (TERMS == 3) {
+                            umma_tf32_ts_2cta(d_tmem, a_hi + j * 8, dl, idesc, 1);
+                            umma_tf32_ts_2cta(d_tmem, a_lo + j * 8, dh, idesc, 1);
+                        }
                     }
                     umma_commit_2cta(&b_empty[s]);
                     umma_commit_2cta(&a_empty[sa]);
@@ -782,14 +797,14 @@ gemm2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) 
                     for (int e = 0; e < 4; ++e) {
                         const uint32_t h = __float_as_uint(x[e]) & 0xFFFFE000u;
                         hi[ch * 4 + e] = h;
-                        lo[ch * 4 + e] = __float_as_uint(x[e] - __uint_as_float(h));
+                        if constexpr (TERMS != 1) lo[ch * 4 + e] = __float_as_uint(x[e] - __uint_as_float(h));
                     }
                 }
                 mbar_wait_cluster(&a_empty[ss], phs ^ 1u);
                 tc_fence_after();
                 const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kTmemAOff + ss * 64);
                 tmem_st32(ta, hi);
-                tmem_st32(ta + 32, lo);
+                if constexpr (TERMS != 1) tmem_st32(ta + 32, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
@@ -814,7 +829,11 @@ gemm2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) 
             const int64_t row = p.row_begin + tile * kGemmBM + quarter * 32 + lane;
             const bool row_ok = row < p.row_end;
             if constexpr (!ARGMAX) {
-                if (etid < BN) thr_s[buf * BN + etid] = p.thr[qb * BN + etid];
+                if (etid < BN) {
+                    float t = p.thr[qb * BN + etid];
+                    if constexpr (TERMS == 1) t -= p.margin[qb * BN + etid];
+                    thr_s[buf * BN + etid] = t;
+                }
                 named_bar_sync(kBarEpilogue, 128);
             } else if (qb == 0) {
                 best = -INFINITY;

@@ -172,7 +172,50 @@ struct CompactParams {
     const int64_t* ids;
     float* D;         // null unless this is the last epoch
     int64_t* I;
+    // filter-and-refine searches (one-term K2 epochs): exact fp32 re-scoring of keys against the row store
+    int rescore;        // 0: keys carry final scores; 1: re-score the epoch's candidates BEFORE the selection
+                        // (they carry one-term filter scores); 2: re-score the k winners AFTER the selection (first
+                        // epoch: selected by 3xTF32 scores) so that every key in the list carries the same arithmetic
+    const float* rows;  // [*, ld] row store the key positions index
+    const float* q;     // [nq, ld] zero-padded queries
+    int ld;
 };
+
+// keys[i] <- make_key(<rows[pos(keys[i])], q>, pos) for i in [0, n): one warp per key, fp32 FMA over float4 lanes and
+// a fixed-order xor-shuffle reduction - the same row and query always give the same bits (exact duplicates tie).
+__device__ __forceinline__ void rescore_keys(uint64_t* keys, int n, const float* rows, const float* qrow, int ld,
+                                             int warp, int nwarps) {
+    const int lane = threadIdx.x & 31;
+    const float4* qv = reinterpret_cast<const float4*>(qrow);
+    const int ld4 = ld >> 2;
+    for (int i = warp; i < n; i += nwarps) {
+        const uint64_t key = keys[i];
+        if (key == 0ull) continue;  // empty slot (uniform per warp)
+        const uint32_t pos = key_pos(key);
+        const float4* rv = reinterpret_cast<const float4*>(rows + (size_t)pos * ld);
+        float acc = 0.f;
+        for (int t = lane; t < ld4; t += 32) {
+            const float4 a = rv[t], b = qv[t];
+            acc = fmaf(a.x, b.x, acc);
+            acc = fmaf(a.y, b.y, acc);
+            acc = fmaf(a.z, b.z, acc);
+            acc = fmaf(a.w, b.w, acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) keys[i] = make_key(acc, pos);
+    }
+}
+
+// rescore == 1: exact scores for the candidates of a one-term epoch.  grid = (nq, gy): the candidates of query
+// blockIdx.x are spread over gy blocks of 8 warps, so the ~k*growth random 3 KB row reads per query run at HBM
+// bandwidth instead of at one SM's latency (inside the compaction CTA they cost ~70 us per epoch).
+__global__ void __launch_bounds__(256) rescore_candidates_kernel(const CompactParams p) {
+    const int q = blockIdx.x;
+    const int ncand = min(p.cnt[q], p.cap);
+    rescore_keys(p.keys + (size_t)q * p.kstride + p.k, ncand, p.rows, p.q + (size_t)q * p.ld, p.ld,
+                 blockIdx.y * 8 + (threadIdx.x >> 5), gridDim.y * 8);
+}
 
 __global__ void __launch_bounds__(kMergeThreads) compact_topk_kernel(const CompactParams p) {
     extern __shared__ __align__(16) unsigned char smem_merge[];
@@ -182,8 +225,18 @@ __global__ void __launch_bounds__(kMergeThreads) compact_topk_kernel(const Compa
     const int64_t q = blockIdx.x;
     const int k = p.k;
     uint64_t* base = p.keys + q * p.kstride;
-    const int64_t M = k + min(p.cnt[q], p.cap);
+    const int ncand = min(p.cnt[q], p.cap);
+    const int64_t M = k + ncand;
+    // (rescore == 1: rescore_candidates_kernel has already rewritten the candidates' scores, grid-wide)
     block_select_topk(buf, p.S, k, M, [&](int64_t c) { return base[c]; }, &cnt);
+    if (p.rescore == 2) {
+        const int P = max(2, pow2_ceil(k));  // <= S
+        for (int j = k + tid; j < P; j += kMergeThreads) buf[j] = 0ull;
+        rescore_keys(buf, k, p.rows, p.q + (size_t)q * p.ld, p.ld, tid >> 5, kMergeThreads / 32);
+        __syncthreads();
+        bitonic_sort_desc<kMergeThreads>(buf, P, 1, tid, -1);
+        __syncthreads();
+    }
     for (int j = tid; j < k; j += kMergeThreads) {
         const uint64_t key = buf[j];
         base[j] = key;
@@ -198,6 +251,42 @@ __global__ void __launch_bounds__(kMergeThreads) compact_topk_kernel(const Compa
         p.thr[q] = kth ? key_score(kth) : -INFINITY;
         p.cnt[q] = 0;
     }
+}
+
+// ---- filter margins ----------------------------------------------------------------------------
+// max over the rows of |x|^2, folded into *out with an integer atomicMax (non-negative floats order like their bits)
+__global__ void row_norm2_max_kernel(const float* rows, int64_t n, int ld, float* out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float best = 0.f;
+    for (int64_t r = w; r < n; r += nw) {
+        const float4* rv = reinterpret_cast<const float4*>(rows + (size_t)r * ld);
+        float acc = 0.f;
+        for (int t = lane; t < (ld >> 2); t += 32) {
+            const float4 a = rv[t];
+            acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        best = fmaxf(best, acc);
+    }
+    if (lane == 0 && best > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(best));
+}
+
+// margin[i] = c * |q_i| * sqrt(max |x|^2) for real queries, 0 for padding (whose threshold is +inf anyway)
+__global__ void query_margin_kernel(const float* q, int nq, int nq_pad, int ld, const float* norm2_max, float c,
+                                    float* margin) {
+    const int lane = threadIdx.x & 31;
+    const int i = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    if (i >= nq_pad) return;
+    float acc = 0.f;
+    if (i < nq)
+        for (int t = lane; t < ld; t += 32) acc += q[(size_t)i * ld + t] * q[(size_t)i * ld + t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    // 1.001: the two square roots and the sums above are themselves rounded
+    if (lane == 0) margin[i] = i < nq ? c * 1.001f * sqrtf(acc) * sqrtf(*norm2_max) : 0.f;
 }
 
 // ---- small utility kernels ---------------------------------------------------------------
