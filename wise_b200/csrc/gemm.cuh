@@ -45,6 +45,12 @@ constexpr int kBarEpilogue = 2;
 
 // Per query-block width BN (UMMA N = 32 / 64 / 128): small batches use a narrow block so the kernel
 // stays bound by the HBM stream of the rows instead of by padded MMAs and query-image traffic.
+// Timing-only experiment knobs for the 1-CTA kernel (results are WRONG when set; never defined in the product build):
+// bit 0: the transform skips LDS + split (stores zeros); bit 1: it also skips the TMEM stores; bit 2: the MMA thread
+// skips the MMAs and only commits.  Used to locate the ~600-cycle per-chunk cost (profiles/r01/gemm_experiments.md).
+#ifndef WB_GEMM_EXP
+#define WB_GEMM_EXP 0
+#endif
 #ifndef WB_GEMM_SLOTS
 #define WB_GEMM_SLOTS(BN) 7  // experiment knob: same-box A/B of 7/6, 6/5 and 5/4 slots (BN 32/64) showed no difference
 #endif
@@ -361,7 +367,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                         const uint32_t a_lo = a_hi + 32;
                         const uint32_t dh0 = desc_lo0 + (uint32_t)s * (uint32_t)(kBBytes >> 4);
 #pragma unroll
-                        for (int j = 0; j < kGemmBK / 8; ++j) {
+                        for (int j = 0; j < ((WB_GEMM_EXP & 4) ? 0 : kGemmBK / 8); ++j) {
                             // one k-step = 8 tf32 = two 16-byte k columns: LBO = kLbo, SBO = 128 B
                             const uint64_t dh = desc_from_words(dh0 + (uint32_t)((j * 2 * kLbo) >> 4), desc_w1);
                             if constexpr (TERMS == 1) {
@@ -409,7 +415,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                 uint32_t hi[32], lo[32];
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
-                    const float4 v = *reinterpret_cast<const float4*>(a_raw + ((ch ^ (r & 7)) << 4));  // SWIZZLE_128B
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if constexpr (!(WB_GEMM_EXP & 1))
+                        v = *reinterpret_cast<const float4*>(a_raw + ((ch ^ (r & 7)) << 4));  // SWIZZLE_128B
                     const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -424,9 +432,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                 mbar_wait(&slot_empty[ss], phs ^ 1u);        // the MMAs that last read this TMEM slot have retired
                 tc_fence_after();
                 const uint32_t ta = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kTmemAOff + ss * 64);
-                tmem_st32(ta, hi);
-                if constexpr (TERMS != 1) tmem_st32(ta + 32, lo);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                if constexpr (!(WB_GEMM_EXP & 2)) {
+                    tmem_st32(ta, hi);
+                    if constexpr (TERMS != 1) tmem_st32(ta + 32, lo);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -498,7 +508,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
 #pragma unroll
                     for (int j = 0; j < kEpi; ++j) {
                         const float sc = __uint_as_float(v[j]);
-                        const bool pass = row_ok && sc > thr_s[buf * BN + cb * kEpi + j];
+                        const bool pass = !(WB_GEMM_EXP & 4) && row_ok && sc > thr_s[buf * BN + cb * kEpi + j];
                         const unsigned m = __ballot_sync(0xffffffffu, pass);
                         if (m) {
                             const int qi = qb * BN + cb * kEpi + j;  // < nq: padded queries have thr = +inf
