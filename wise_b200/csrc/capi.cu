@@ -488,7 +488,6 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     const int nchunks = (ld + kGemmBK - 1) / kGemmBK;
     const int nqb = (int)((nq + kGemmBN - 1) / kGemmBN);
     const int kstride = k + cap;
-    // measured (profiles/r01/gemm_experiments.md): the CTA pair wins from 64 queries up, the single CTA below
     // measured (10M x 768): 40 / 64 queries 5.9 / 6.3 ms on one CTA vs 6.2 / 6.4 ms on the pair; 128 queries 8.8 vs 8.1 ms
     const bool use2 = BN >= 128 && env_int("WB_GEMM_2CTA", 1) != 0 && (h->sm_count % 2) == 0;
     TRY(h->gimg.ensure((size_t)nqb * nchunks * kGemmBBytes));
