@@ -7,28 +7,30 @@
 // IVF coarse quantizer / add-time assignment and the k-means assignment (k = 1).
 //
 // S[row, q] = sum_t X[row, t] * Q[q, t],  X = database rows (A operand, M = 128 rows per tile),
-// Q = a block of BN = 128 queries (B operand), both K-major.  x*y ~= xh*yh + xh*yl + xl*yh with
-// xh = tf32-truncated x, xl = x - xh (exact in fp32): three MMAs per k-step into one fp32
-// accumulator in TMEM; the dropped xl*yl term is < 2^-20 relative.
+// Q = a block of BN = 16 / 32 / 64 / 128 queries (B operand), both K-major.  x*y ~= xh*yh + xh*yl + xl*yh with
+// xh = tf32-truncated x, xl = x - xh (exact in fp32): three terms per k-step into one fp32 accumulator in TMEM
+// (issued as two MMAs for BN <= 64, see FOLD); the dropped xl*yl term is < 2^-20 relative.
+// TERMS = 1 ("filter" epochs of a search, see the kernel): only xh*yh, candidates re-scored exactly afterwards.
 //
 // One persistent CTA per SM, 16 warps:
 //   warp 0      producer A: per 32-float k-chunk one 2-D TMA load of the raw fp32 row tile
 //                          (128 x 128 B, SWIZZLE_128B) into a deep ring freed by the transform warps
 //   warp 3      producer B: one bulk copy of the pre-split query image per chunk into the operand slots
-//   warps 4-7, 12-15 transform (two sets on alternate chunks): thread = row; reads its 128 B of the swizzled tile (conflict-free),
-//                          splits hi/lo and stores both straight into TENSOR MEMORY (tcgen05.st):
+//   warps 4-7, 12-15 transform (two sets on alternate chunks): thread = row; reads its 128 B of the swizzled tile
+//                          (conflict-free), splits hi/lo and stores both straight into TENSOR MEMORY (tcgen05.st):
 //                          the A operand never goes back to shared memory
-//   warp 1      MMA      : one thread issues 12 tcgen05.mma (A from TMEM, B from a no-swizzle K-major
-//                          shared-memory descriptor) per chunk; tcgen05.commit releases the stage
-//   warps 8-11  epilogue : tcgen05.ld of the finished 128x128 fp32 tile (double-buffered in TMEM, so
-//                          it overlaps the next tile's MMAs); a score survives only if it beats the
-//                          query's current k-th best; survivors are appended to a per-query
+//   warp 1      MMA      : waits on ONE barrier per slot (4 transform arrivals + the image's transaction bytes), one
+//                          elected thread issues the chunk's tcgen05.mma (A from TMEM, B from a no-swizzle K-major
+//                          shared-memory descriptor); tcgen05.commit releases the slot
+//   warps 8-11  epilogue : tcgen05.ld of the finished tile (double-buffered in TMEM, so it overlaps the next
+//                          tile's MMAs); a score survives only if it beats the query's current k-th best
+//                          (minus the filter margin for TERMS = 1); survivors are appended to a per-query
 //                          candidate list in global memory (warp-aggregated atomics)
 //   warp 2      TMEM allocator.
 // Scores never go to HBM.  The host runs the database in growing "epochs"; between epochs
 // compact_topk_kernel (merge.cuh) folds the candidates into the per-query top-k and tightens the
-// thresholds, so the expected number of survivors per epoch stays ~3k per query.
-// Algorithmic work: 2*nq*N*d flop (the split issues 3x that on the tensor pipe).
+// thresholds; an epoch yields ~k * growth (~1000) candidates per query.
+// Algorithmic work: 2*nq*N*d flop (3x that is issued in 3xTF32 epochs, 1x in filter epochs).
 #pragma once
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 
@@ -43,8 +45,9 @@ constexpr int kGemmABytes = kGemmBM * kGemmBK * 4;       // 16 KB raw row tile
 constexpr int kTmemCols = 512;
 constexpr int kBarEpilogue = 2;
 
-// Per query-block width BN (UMMA N = 32 / 64 / 128): small batches use a narrow block so the kernel
+// Per query-block width BN (UMMA N = 16 / 32 / 64 / 128): small batches use a narrow block so the kernel
 // stays bound by the HBM stream of the rows instead of by padded MMAs and query-image traffic.
+//
 // Timing-only experiment knobs for the 1-CTA kernel (results are WRONG when set; never defined in the product build):
 // bit 0: the transform skips LDS + split (stores zeros); bit 1: it also skips the TMEM stores; bit 2: the MMA thread
 // skips the MMAs and only commits.  Used to locate the ~600-cycle per-chunk cost (profiles/r01/gemm_experiments.md).
