@@ -202,3 +202,73 @@ def test_fast_reader_pickle_protocols(tmp_path, protocol):
     ids = np.empty(5, np.int64); out = np.empty((5, 33), np.float32); n = C.c_int64()
     assert L.wb_tar_read(str(fn).encode(), 33, 5, _capi.ptr(ids), _capi.ptr(out), C.byref(n)) == 0
     assert np.array_equal(out, x[:, 0, :]) and ids.tolist() == [10, 11, 12, 13, 14]
+
+
+def _read_c_abi(fn, d, cap):
+    import ctypes as C
+    from wise_b200 import _capi
+    L = _capi.lib()
+    rows, members, dd = C.c_int64(), C.c_int64(), C.c_int64()
+    assert L.wb_tar_scan(str(fn).encode(), C.byref(rows), C.byref(members), C.byref(dd)) == 0, L.wb_last_error()
+    ids = np.full(cap, -7, np.int64); out = np.zeros((cap, d), np.float32); n = C.c_int64()
+    assert L.wb_tar_read(str(fn).encode(), d, cap, _capi.ptr(ids), _capi.ptr(out), C.byref(n)) == 0, L.wb_last_error()
+    return rows.value, members.value, dd.value, ids[: n.value], out[: n.value]
+
+
+def test_fast_reader_threads_agree(tmp_path, monkeypatch):
+    """The fixed-stride plan decodes a regular shard on several threads (one per 2048 samples, at most 16):
+    the result does not depend on the thread count."""
+    x = _write_store(tmp_path, 9000, 24, 100000)
+    fn = tmp_path / "video-000000.tar"
+    got = {}
+    for t in ("1", "3", "16"):
+        monkeypatch.setenv("WISE_B200_LOADER_THREADS", t)
+        got[t] = _read_c_abi(fn, 24, 9000)
+        assert got[t][:3] == (9000, 9000, 24)
+        assert np.array_equal(got[t][4], x) and np.array_equal(got[t][3], 3 * np.arange(9000) + 1)
+
+
+def test_fast_reader_irregular_shards_take_the_sequential_walk(tmp_path):
+    """Anything that breaks the fixed stride - samples with different row counts, a foreign member between two
+    samples - fails the per-member verification of the plan and is decoded by the sequential walker instead."""
+    import io
+    rng = np.random.default_rng(3)
+    parts = [rng.standard_normal((m, 8)).astype(np.float32) for m in (1, 2, 1, 3, 1)]
+    fn = tmp_path / "video-000000.tar"
+    with tarfile.open(fn, "w") as tf:
+        for i, a in enumerate(parts):
+            data = pickle.dumps(a)
+            ti = tarfile.TarInfo("%010d.features.pyd" % (i * 5))
+            ti.size = len(data)
+            ti.mtime = 1700000000.25 + i  # float mtime: python writes a pax extended header per member
+            tf.addfile(ti, io.BytesIO(data))
+            if i == 2:
+                junk = b'{"note": "not a feature"}'
+                tj = tarfile.TarInfo("%010d.json" % (i * 5))
+                tj.size = len(junk)
+                tf.addfile(tj, io.BytesIO(junk))
+    rows, members, d, ids, out = _read_c_abi(fn, 8, 8)
+    assert (rows, members, d) == (8, 5, 8)
+    assert np.array_equal(out, np.concatenate(parts)) and ids.tolist() == [0, 5, 5, 10, 15, 15, 15, 20]
+    # same key width and payload, but one member is not a feature file: the plan's name check must reject it
+    fn2 = tmp_path / "video-000001.tar"
+    a = rng.standard_normal((6, 1, 8)).astype(np.float32)
+    with tarfile.open(fn2, "w") as tf:
+        for i in range(6):
+            data = pickle.dumps(a[i])
+            ti = tarfile.TarInfo(("%010d.features.pyd" if i != 3 else "%010d.featurez.pyd") % i)
+            ti.size = len(data)
+            tf.addfile(ti, io.BytesIO(data))
+    rows, members, d, ids, out = _read_c_abi(fn2, 8, 6)
+    assert (rows, members) == (5, 5) and ids.tolist() == [0, 1, 2, 4, 5]
+    assert np.array_equal(out, a[[0, 1, 2, 4, 5], 0, :])
+
+
+def test_iter_batch_shard_aligned(tmp_path):
+    """exact=False never copies across shards: batches end at shard boundaries and still cover every row in order."""
+    x = _write_store(tmp_path, 2500, 16, 1000)
+    r = WebdatasetStore("video", tmp_path)
+    r.enable_read()
+    bi, bx = zip(*r.iter_batch(batch_size=600, exact=False))
+    assert [len(b) for b in bi] == [600, 400, 600, 400, 500]
+    assert np.array_equal(np.concatenate(bx), x) and np.array_equal(np.concatenate(bi), 3 * np.arange(2500) + 1)

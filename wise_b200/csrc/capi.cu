@@ -1422,6 +1422,16 @@ extern "C" int wb_tar_scan(const char* path, int64_t* rows_out, int64_t* members
     if (!path) return fail("NULL path");
     int64_t rows = 0, members = 0, d = -1;
     std::string why;
+    {   // fixed-stride shards (what WebdatasetStore writes): verified member by member, on several threads
+        wbtar::Mapped mp;
+        wbtar::Plan pl;
+        if (mp.open(path) && wbtar::make_plan(mp, &pl) && wbtar::for_each_member(mp, pl, [](int64_t, int64_t) {})) {
+            if (rows_out) *rows_out = pl.count * pl.m;
+            if (members_out) *members_out = pl.count;
+            if (d_out) *d_out = pl.d;
+            return 0;
+        }
+    }
     const int rc = wbtar::walk(path, [&](const wbtar::Sample& s) {
         if (d < 0) d = s.d;
         if (s.d != d) return 2;
@@ -1442,6 +1452,22 @@ extern "C" int wb_tar_read(const char* path, int64_t d, int64_t cap, int64_t* id
     if (!path || !ids || !x || !rows_out) return fail("NULL argument");
     int64_t n = 0;
     std::string why;
+    {
+        wbtar::Mapped mp;
+        wbtar::Plan pl;
+        if (mp.open(path) && wbtar::make_plan(mp, &pl) && pl.d == d && pl.count * pl.m <= cap) {
+            const size_t row_bytes = (size_t)pl.m * (size_t)d * 4;
+            const bool ok = wbtar::for_each_member(mp, pl, [&](int64_t j, int64_t id) {
+                memcpy(reinterpret_cast<unsigned char*>(x) + (size_t)j * row_bytes,
+                       mp.p + (size_t)j * pl.stride + pl.pre + 512 + pl.data_off, row_bytes);
+                for (int64_t r = 0; r < pl.m; ++r) ids[j * pl.m + r] = id;
+            });
+            if (ok) {
+                *rows_out = pl.count * pl.m;
+                return 0;
+            }
+        }
+    }
     const int rc = wbtar::walk(path, [&](const wbtar::Sample& s) {
         if (s.d != d) { why = "dimension changes inside the shard"; return 2; }
         if (n + s.m > cap) { why = "buffer too small"; return 1; }

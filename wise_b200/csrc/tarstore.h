@@ -13,7 +13,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace wbtar {
@@ -111,7 +113,9 @@ struct Mapped {
         if (fstat(fd, &st) != 0) return false;
         n = (size_t)st.st_size;
         if (n == 0) return true;
-        void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        // MAP_POPULATE: the page tables are filled in bulk at map time; walking a shard whose members are one page
+        // each otherwise takes one minor fault per sample (measured: 0.09 -> 0.03 s per 256 MB shard)
+        void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
         if (m == MAP_FAILED) return false;
         madvise(m, n, MADV_SEQUENTIAL);
         p = (const unsigned char*)m;
@@ -173,6 +177,141 @@ inline int walk(const char* path, F fn, std::string* why) {
         off = next;
     }
     return 0;
+}
+
+// ---- fixed-stride fast path ----------------------------------------------------------------------
+// A shard written by WebdatasetStore.add holds members of identical size: same key width (%010d), same pickle
+// prologue, same (m, d) payload, each preceded by the same one-block pax extended header (python's tarfile writes
+// one for the float mtime) - so sample j starts at j * stride and its float data at a fixed offset inside it.
+// The plan is derived from the first member and every member is verified against it (size field, type flag, name
+// suffix, pickle prologue bytes); any mismatch makes the caller fall back to the sequential walk() above.  With a
+// plan the members are independent, so the decode runs on several threads: one thread is latency-bound on the
+// ~12 cache lines of header + pickle prologue per sample (~1.5 us per sample, measured), not on bandwidth.
+struct Plan {
+    size_t stride = 0;     // bytes between samples (pax header + its block, member header, padded payload)
+    size_t pre = 0;        // bytes of pax extended header in front of the member header (0 or 1024)
+    size_t size = 0;       // payload bytes of a member (pickle)
+    size_t data_off = 0;   // offset of the float data inside the payload
+    size_t name_len = 0;   // length of the member name
+    size_t key_len = 0;    // digits before the first '.'
+    int64_t m = 0, d = 0;  // rows per sample, dimension
+    int64_t count = 0;     // members in the shard
+};
+
+inline bool parse_size(const unsigned char* h, uint64_t* size) {
+    uint64_t v = 0;
+    if (h[124] & 0x80) {
+        for (int i = 125; i < 136; ++i) v = (v << 8) | h[i];
+    } else {
+        for (int i = 124; i < 136 && h[i] >= '0' && h[i] <= '7'; ++i) v = v * 8 + (h[i] - '0');
+    }
+    *size = v;
+    return true;
+}
+
+inline bool is_zero_block(const unsigned char* h) {
+    for (int i = 0; i < 512; ++i)
+        if (h[i]) return false;
+    return true;
+}
+
+inline bool make_plan(const Mapped& mp, Plan* pl) {
+    if (mp.n < 2048) return false;
+    const unsigned char* h = mp.p;
+    if (is_zero_block(h)) return false;
+    size_t pre = 0;
+    if ((char)h[156] == 'x') {  // per-member pax header: one header block + one block of records
+        uint64_t xs = 0;
+        parse_size(h, &xs);
+        if (xs == 0 || xs > 512) return false;
+        pre = 1024;
+        h = mp.p + pre;
+    }
+    const char type = (char)h[156];
+    if (!(type == '0' || type == 0)) return false;
+    const size_t nl = strnlen((const char*)h, 100);
+    static const char kSuffix[] = ".features.pyd";
+    const size_t sl = sizeof(kSuffix) - 1;
+    if (nl <= sl || memcmp(h + nl - sl, kSuffix, sl) != 0) return false;
+    size_t key = 0;
+    while (key < nl && h[key] >= '0' && h[key] <= '9') ++key;  // no directory part, digits then ".features.pyd"
+    if (key == 0 || key + sl != nl) return false;
+    uint64_t size = 0;
+    parse_size(h, &size);
+    if (size == 0 || pre + 512 + size > mp.n) return false;
+    Sample s{};
+    if (!scan_ndarray_pickle(h + 512, size, &s)) return false;
+    pl->pre = pre;
+    pl->stride = pre + 512 + ((size + 511) & ~(size_t)511);
+    pl->size = size;
+    pl->data_off = (size_t)(s.data - (h + 512));
+    pl->name_len = nl;
+    pl->key_len = key;
+    pl->m = s.m;
+    pl->d = s.d;
+    int64_t count = (int64_t)(mp.n / pl->stride);
+    while (count > 0 && is_zero_block(mp.p + (size_t)(count - 1) * pl->stride)) --count;  // end-of-archive padding
+    if (count <= 0) return false;
+    // what follows the last member must be the end-of-archive marker (or the end of the file)
+    const size_t tail = (size_t)count * pl->stride;
+    if (tail + 512 <= mp.n && !is_zero_block(mp.p + tail)) return false;
+    pl->count = count;
+    return true;
+}
+
+// member j against the plan; on success *id is its key
+inline bool check_member(const Mapped& mp, const Plan& pl, int64_t j, int64_t* id) {
+    const unsigned char* g = mp.p + (size_t)j * pl.stride;
+    if (pl.pre) {  // the pax header may differ in its records (mtime digits) but must stay one block
+        uint64_t xs = 0;
+        if ((char)g[156] != 'x') return false;
+        parse_size(g, &xs);
+        if (xs == 0 || xs > 512) return false;
+    }
+    const unsigned char* h = g + pl.pre;
+    const unsigned char* h0 = mp.p + pl.pre;
+    if (memcmp(h + 124, h0 + 124, 12) != 0 || h[156] != h0[156]) return false;             // size field, type flag
+    if (h[pl.name_len] != 0 || memcmp(h + pl.key_len, h0 + pl.key_len, pl.name_len - pl.key_len) != 0) return false;
+    int64_t v = 0;
+    for (size_t i = 0; i < pl.key_len; ++i) {
+        if (h[i] < '0' || h[i] > '9') return false;
+        v = v * 10 + (h[i] - '0');
+    }
+    if (memcmp(h + 512, h0 + 512, pl.data_off) != 0) return false;                          // identical pickle prologue
+    *id = v;
+    return true;
+}
+
+inline int loader_threads(int64_t count) {
+    int t = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("WISE_B200_LOADER_THREADS")) t = atoi(e);
+    t = t < 1 ? 1 : (t > 16 ? 16 : t);
+    const int64_t by_work = count / 2048 + 1;
+    return (int)(by_work < t ? by_work : t);
+}
+
+// Runs fn(j, id) for every member on several threads; false if any member deviates from the plan.
+template <class F>
+inline bool for_each_member(const Mapped& mp, const Plan& pl, F fn) {
+    const int T = loader_threads(pl.count);
+    std::atomic<bool> ok{true};
+    auto work = [&](int t) {
+        const int64_t j0 = pl.count * t / T, j1 = pl.count * (t + 1) / T;
+        for (int64_t j = j0; j < j1 && ok.load(std::memory_order_relaxed); ++j) {
+            int64_t id;
+            if (!check_member(mp, pl, j, &id)) { ok = false; return; }
+            fn(j, id);
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    return ok;
 }
 
 }  // namespace wbtar

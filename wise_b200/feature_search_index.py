@@ -118,7 +118,9 @@ class FeatureSearchIndex(SearchIndex):
         self._say("Adding feature vectors to index")
         index.reserve(feature_count)
         # the reference adds 512 rows per call (iter_batch default); larger batches amortise the call overhead
-        for ids_batch, vectors_batch in feature_store.iter_batch(batch_size=65536):
+        batches = (feature_store.iter_batch(batch_size=65536, exact=False) if isinstance(feature_store, WebdatasetStore)
+                   else feature_store.iter_batch(batch_size=65536))
+        for ids_batch, vectors_batch in batches:
             index.add_with_ids(np.ascontiguousarray(vectors_batch, np.float32), np.ascontiguousarray(ids_batch, np.int64))
         faiss.write_index(index, index_fn.as_posix())
         self._say(f"  saved index to {index_fn}")

@@ -204,46 +204,76 @@ class WebdatasetStore(FeatureStore):
     def __iter__(self):
         yield from self._maybe_shuffled()
 
-    def _fast_shards(self):
-        """Whole shards decoded by the C++ reader: yields (ids int64[n], x float32[n, d]) or None when a shard
-        needs the python reader.  Only for the un-shuffled, one-row-per-sample layout WISE writes."""
+    def _decode_shard(self, fn):
+        """One whole shard through the C++ reader: (ids int64[n], x float32[n, d]), or None when the shard needs
+        the python reader.  The ctypes call releases the GIL, so a background thread can run it."""
         import ctypes as C
         fast = _fast_tar()
-        for fn in self.shard_files():
-            rows = getattr(self, "_shard_rows", {}).get(fn)
-            if fast is None or rows is None or self.feature_dim <= 0:
-                yield fn, None
-                continue
-            ids = np.empty(rows, np.int64)
-            x = np.empty((rows, self.feature_dim), np.float32)
-            n = C.c_int64()
-            rc = fast[0].wb_tar_read(fn.encode(), self.feature_dim, rows, fast[1].ptr(ids), fast[1].ptr(x), C.byref(n))
-            yield fn, ((ids[: n.value], x[: n.value]) if rc == 0 else None)
+        rows = getattr(self, "_shard_rows", {}).get(fn)
+        if fast is None or rows is None or self.feature_dim <= 0:
+            return None
+        ids = np.empty(rows, np.int64)
+        x = np.empty((rows, self.feature_dim), np.float32)
+        n = C.c_int64()
+        rc = fast[0].wb_tar_read(fn.encode(), self.feature_dim, rows, fast[1].ptr(ids), fast[1].ptr(x), C.byref(n))
+        return (ids[: n.value], x[: n.value]) if rc == 0 else None
 
-    def iter_batch(self, batch_size=512):
+    def _fast_shards(self):
+        """(fn, decoded) per shard, un-shuffled order; shard i+1 is decoded on a helper thread while the caller
+        consumes shard i (only for the one-row-per-sample fp32 layout WISE writes; others yield None)."""
+        from concurrent.futures import ThreadPoolExecutor
+        files = list(self.shard_files())
+        if not files:
+            return
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            nxt = pool.submit(self._decode_shard, files[0])
+            for i, fn in enumerate(files):
+                dec = nxt.result()
+                if i + 1 < len(files):
+                    nxt = pool.submit(self._decode_shard, files[i + 1])
+                yield fn, dec
+
+    def _python_shard(self, fn):
+        li, lx = [], []
+        with tarfile.open(fn) as tf:
+            for m in tf:
+                key, _, ext = os.path.basename(m.name).partition(".")
+                if m.isreg() and ext == "features.pyd":
+                    v = decode_features(tf.extractfile(m).read())
+                    li.append(int(key)); lx.append(np.squeeze(v, axis=0))
+        if not li:
+            return np.empty(0, np.int64), np.empty((0, self.feature_dim), np.float32)
+        return np.asarray(li, np.int64), np.stack(lx).astype(np.float32)
+
+    def iter_batch(self, batch_size=512, exact=True):
         """(ids int64[b], features float32[b, d]) batches; (1, d) samples squeezed like :131-139.
-        Un-shuffled reads go through the C++ shard reader (one pass per shard, no per-vector python objects)."""
+        Un-shuffled reads go through the C++ shard reader (one pass per shard, no per-vector python objects);
+        batches are views into the decoded shard, only a batch that straddles two shards is copied.
+        exact=False (index builds, which accept any batch length) ends a batch at every shard boundary instead."""
         if (not self.shard_shuffle and not self.shuffle_values and getattr(self, "_shard_rows", None)
                 and os.environ.get("WISE_B200_FAST_STORE", "1") != "0"):
             carry_i, carry_x = None, None
             for fn, dec in self._fast_shards():
-                if dec is None:  # this shard in python
-                    li, lx = [], []
-                    with tarfile.open(fn) as tf:
-                        for m in tf:
-                            key, _, ext = os.path.basename(m.name).partition(".")
-                            if m.isreg() and ext == "features.pyd":
-                                v = decode_features(tf.extractfile(m).read())
-                                li.append(int(key)); lx.append(np.squeeze(v, axis=0))
-                    dec = (np.asarray(li, np.int64), np.stack(lx).astype(np.float32)) if li else (np.empty(0, np.int64), np.empty((0, self.feature_dim), np.float32))
-                ids, x = dec
-                if carry_i is not None and carry_i.size:
-                    ids, x = np.concatenate([carry_i, ids]), np.concatenate([carry_x, x])
-                full = (ids.shape[0] // batch_size) * batch_size
-                for s in range(0, full, batch_size):
-                    yield ids[s:s + batch_size], x[s:s + batch_size]
+                ids, x = dec if dec is not None else self._python_shard(fn)
+                pos = 0
+                if carry_i is not None and carry_i.shape[0]:
+                    take = min(batch_size - carry_i.shape[0], ids.shape[0])
+                    carry_i = np.concatenate([carry_i, ids[:take]])
+                    carry_x = np.concatenate([carry_x, x[:take]])
+                    pos = take
+                    if carry_i.shape[0] < batch_size:
+                        continue  # the shard was too small to complete the batch
+                    yield carry_i, carry_x
+                    carry_i, carry_x = None, None
+                full = pos + ((ids.shape[0] - pos) // batch_size) * batch_size
+                for s0 in range(pos, full, batch_size):
+                    yield ids[s0:s0 + batch_size], x[s0:s0 + batch_size]
+                if not exact:
+                    if full < ids.shape[0]:
+                        yield ids[full:], x[full:]
+                    continue
                 carry_i, carry_x = ids[full:], x[full:]
-            if carry_i is not None and carry_i.size:
+            if carry_i is not None and carry_i.shape[0]:
                 yield carry_i, carry_x
             return
         ids, vecs = [], []
