@@ -48,6 +48,22 @@ def _need(f, n: int) -> bytes:
     return b
 
 
+def _read_array(f, count: int, dtype) -> np.ndarray:
+    """`count` items of `dtype` read straight into a fresh array (no intermediate bytes object)."""
+    a = np.empty(count, dtype)
+    if count:
+        got = f.readinto(memoryview(a).cast("B"))
+        if got != a.nbytes:
+            raise RuntimeError(f"read error in index file: wanted {a.nbytes} bytes, got {got}")
+    return a
+
+
+def _write_array(f, a: np.ndarray) -> None:
+    a = np.ascontiguousarray(a)
+    if a.size:
+        f.write(memoryview(a).cast("B"))  # no .tobytes() copy of multi-GB blocks
+
+
 def _write_flat(f, index, centroids: np.ndarray | None = None) -> None:
     """IxFI block for an IndexFlatIP (or for an IVF quantizer given its centroid table)."""
     f.write(b"IxFI")
@@ -55,14 +71,14 @@ def _write_flat(f, index, centroids: np.ndarray | None = None) -> None:
         n, d = centroids.shape
         _hdr(f, d, n, True, fc.METRIC_INNER_PRODUCT)
         f.write(struct.pack("<Q", n * d))
-        f.write(np.ascontiguousarray(centroids, np.float32).tobytes())
+        _write_array(f, np.ascontiguousarray(centroids, np.float32))
         return
     n, d = index.ntotal, index.d
     _hdr(f, d, n, True, fc.METRIC_INNER_PRODUCT)
     f.write(struct.pack("<Q", n * d))
     for s in range(0, n, _CHUNK_ROWS):
         x, _, _ = index._export(s, min(_CHUNK_ROWS, n - s))
-        f.write(x.tobytes())
+        _write_array(f, x)
 
 
 def write_index(index, fname: str) -> None:
@@ -76,7 +92,7 @@ def write_index(index, fname: str) -> None:
             f.write(struct.pack("<Q", n))
             for s in range(0, n, _CHUNK_ROWS):
                 _, ids, _ = index._export(s, min(_CHUNK_ROWS, n - s))
-                f.write(ids.tobytes())
+                _write_array(f, ids)
         elif isinstance(index, fc.IndexFlatIP):
             _write_flat(f, index)
         elif isinstance(index, fc.IndexIVFFlat):
@@ -135,8 +151,8 @@ def _write_ivf(f, index) -> None:
         rows = order[pos:pos + m]
         pos += m
         for s in range(0, m, _CHUNK_ROWS):
-            f.write(_gather_rows(index, rows[s:s + _CHUNK_ROWS]).tobytes())
-        f.write(ids[rows].tobytes())
+            _write_array(f, _gather_rows(index, rows[s:s + _CHUNK_ROWS]))
+        _write_array(f, ids[rows])
 
 
 def _gather_rows(index, rows: np.ndarray) -> np.ndarray:
@@ -177,8 +193,7 @@ def _read_flat_body(f, add_rows) -> tuple[int, int]:
 def _stream_rows(f, d: int, n: int, sink) -> None:
     for s in range(0, n, _CHUNK_ROWS):
         m = min(_CHUNK_ROWS, n - s)
-        x = np.frombuffer(_need(f, m * d * 4), np.float32).reshape(m, d)
-        sink(s, x)
+        sink(s, _read_array(f, m * d, np.float32).reshape(m, d))
 
 
 def _read_any(f):
@@ -216,9 +231,9 @@ def _read_any(f):
         for s in range(0, n, _CHUNK_ROWS):
             m = min(_CHUNK_ROWS, n - s)
             f.seek(rows_at + s * d * 4)
-            x = np.frombuffer(_need(f, m * d * 4), np.float32).reshape(m, d)
+            x = _read_array(f, m * d, np.float32).reshape(m, d)
             f.seek(ids_at + s * 8)
-            ids = np.frombuffer(_need(f, m * 8), np.int64)
+            ids = _read_array(f, m, np.int64)
             idmap.add_with_ids(x, ids)
         return idmap
     if tag == b"IwFl":
@@ -273,12 +288,12 @@ def _read_ivf(f):
         codes_at = f.tell()
         ids_at = codes_at + m * d * 4
         f.seek(ids_at)
-        ids = np.frombuffer(_need(f, m * 8), np.int64)
+        ids = _read_array(f, m, np.int64)
         end = f.tell()
         for s in range(0, m, _CHUNK_ROWS):
             mm = min(_CHUNK_ROWS, m - s)
             f.seek(codes_at + s * d * 4)
-            x = np.frombuffer(_need(f, mm * d * 4), np.float32).reshape(mm, d)
+            x = _read_array(f, mm * d, np.float32).reshape(mm, d)
             a = np.full(mm, l, np.int32)
             ids_c = np.ascontiguousarray(ids[s:s + mm])  # keep a reference: the C call borrows this buffer
             _capi.check(_capi.lib().wb_ivf_add_preassigned(index._h, mm, _capi.ptr(x), _capi.ptr(ids_c), _capi.ptr(a)))
