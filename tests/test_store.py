@@ -1,5 +1,6 @@
 """FeatureStore layout tests, mirroring /root/reference/src/feature/store/test_feature_store.py,
 plus the fixture written by the reference's own NumpySaveStore (tests/golden/make_golden.py)."""
+import itertools
 import os
 import pickle
 import tarfile
@@ -272,3 +273,26 @@ def test_iter_batch_shard_aligned(tmp_path):
     bi, bx = zip(*r.iter_batch(batch_size=600, exact=False))
     assert [len(b) for b in bi] == [600, 400, 600, 400, 500]
     assert np.array_equal(np.concatenate(bx), x) and np.array_equal(np.concatenate(bi), 3 * np.arange(2500) + 1)
+
+
+def test_shard_shuffled_batches_follow_the_sample_stream(tmp_path):
+    """shard_shuffle=True (the IVF training sample of create_index): iter_batch visits the shards in the same
+    shuffled order as the per-sample iterator, through the C++ reader."""
+    import random
+    x = _write_store(tmp_path, 2300, 12, 500)
+    a = WebdatasetStore("video", tmp_path)
+    a.enable_read(shard_shuffle=True)
+    random.seed(77)
+    ids_stream = [i for i, _ in itertools.islice(a, 1200)]
+    b = WebdatasetStore("video", tmp_path)
+    b.enable_read(shard_shuffle=True)
+    assert b._shard_rows
+    random.seed(77)
+    got_i, got_x = [], []
+    for bi, bx in b.iter_batch(batch_size=400, exact=False):
+        got_i.append(bi); got_x.append(bx)
+        if sum(len(g) for g in got_i) >= 1200:
+            break
+    got_i, got_x = np.concatenate(got_i)[:1200], np.concatenate(got_x)[:1200]
+    assert got_i.tolist() == ids_stream
+    assert np.array_equal(got_x, x[(got_i - 1) // 3])

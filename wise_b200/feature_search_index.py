@@ -108,8 +108,19 @@ class FeatureSearchIndex(SearchIndex):
             shuffled = type(feature_store)(self.media_type, self.features_dir)
             shuffled.enable_read(shard_shuffle=True)
             train_features = np.ndarray((train_count, feature_dim), dtype=np.float32)
-            for i, (_, vec) in enumerate(itertools.islice(shuffled, train_count)):
-                train_features[i, :] = vec
+            if isinstance(shuffled, WebdatasetStore):
+                # same sample as the reference's islice over the shard-shuffled stream (:66-71), read shard-wise
+                got = 0
+                for _, xb in shuffled.iter_batch(batch_size=65536, exact=False):
+                    take = min(xb.shape[0], train_count - got)
+                    train_features[got:got + take] = xb[:take]
+                    got += take
+                    if got == train_count:
+                        break
+                assert got == train_count
+            else:
+                for i, (_, vec) in enumerate(itertools.islice(shuffled, train_count)):
+                    train_features[i, :] = vec
             assert not index.is_trained
             self._say(f"  training {index_type} index with {train_count} features with {cell_count} clusters ...")
             index.train(train_features)

@@ -219,10 +219,12 @@ class WebdatasetStore(FeatureStore):
         return (ids[: n.value], x[: n.value]) if rc == 0 else None
 
     def _fast_shards(self):
-        """(fn, decoded) per shard, un-shuffled order; shard i+1 is decoded on a helper thread while the caller
-        consumes shard i (only for the one-row-per-sample fp32 layout WISE writes; others yield None)."""
+        """(fn, decoded) per shard, in shard order (shuffled when shard_shuffle is set); shard i+1 is decoded on a
+        helper thread while the caller consumes shard i (only for the fp32 layout WISE writes; others yield None)."""
         from concurrent.futures import ThreadPoolExecutor
         files = list(self.shard_files())
+        if self.shard_shuffle:
+            random.shuffle(files)  # same shard-order shuffle as _samples(); rows stay in order inside a shard
         if not files:
             return
         with ThreadPoolExecutor(max_workers=1) as pool:
@@ -250,7 +252,7 @@ class WebdatasetStore(FeatureStore):
         Un-shuffled reads go through the C++ shard reader (one pass per shard, no per-vector python objects);
         batches are views into the decoded shard, only a batch that straddles two shards is copied.
         exact=False (index builds, which accept any batch length) ends a batch at every shard boundary instead."""
-        if (not self.shard_shuffle and not self.shuffle_values and getattr(self, "_shard_rows", None)
+        if (not self.shuffle_values and getattr(self, "_shard_rows", None)
                 and os.environ.get("WISE_B200_FAST_STORE", "1") != "0"):
             carry_i, carry_x = None, None
             for fn, dec in self._fast_shards():
