@@ -37,7 +37,7 @@ inline bool scan_ndarray_pickle(const unsigned char* p, size_t n, Sample* out) {
     const unsigned char* best = nullptr;
     size_t best_len = 0;
     bool f4 = false, last_bool = false, fortran = false, order_f = false;
-    auto need = [&](size_t k) { return i + k <= n; };
+    auto need = [&](size_t k) { return k <= n - i; };  // i <= n always; overflow-safe for 64-bit lengths from the file
     while (i < n) {
         const unsigned char op = p[i++];
         switch (op) {
@@ -95,7 +95,8 @@ inline bool scan_ndarray_pickle(const unsigned char* p, size_t n, Sample* out) {
     // the boolean right before the data bytes is the state tuple's is_fortran flag
     if (!best || !f4 || fortran || order_f || ndim < 1) return false;
     if (ndim == 1) { shape[1] = shape[0]; shape[0] = 1; }  // a bare (d,) vector counts as one row
-    if (shape[0] <= 0 || shape[1] <= 0 || (size_t)(shape[0] * shape[1] * 4) != best_len) return false;
+    if (shape[0] <= 0 || shape[1] <= 0 || shape[0] > (1ll << 30) || shape[1] > (1ll << 30)) return false;
+    if ((size_t)(shape[0] * shape[1] * 4) != best_len) return false;
     out->data = best;
     out->m = shape[0];
     out->d = shape[1];
@@ -152,7 +153,7 @@ inline int walk(const char* path, F fn, std::string* why) {
         }
         const char type = (char)h[156];
         const size_t data = off + 512;
-        if (data + size > mp.n) { *why = "truncated tar member"; return 3; }
+        if (size > mp.n - data) { *why = "truncated tar member"; return 3; }  // (no overflow: data <= mp.n)
         const size_t next = data + ((size + 511) & ~(size_t)511);
         if (type == 'L') {  // GNU long name for the next member
             longname.assign((const char*)mp.p + data, strnlen((const char*)mp.p + data, size));
@@ -238,7 +239,7 @@ inline bool make_plan(const Mapped& mp, Plan* pl) {
     if (key == 0 || key + sl != nl) return false;
     uint64_t size = 0;
     parse_size(h, &size);
-    if (size == 0 || pre + 512 + size > mp.n) return false;
+    if (size == 0 || size > mp.n - pre - 512) return false;  // (no overflow: mp.n >= 2048)
     Sample s{};
     if (!scan_ndarray_pickle(h + 512, size, &s)) return false;
     pl->pre = pre;
