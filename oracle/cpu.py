@@ -37,6 +37,8 @@ def lib():
                                      C.c_int64, fp, ip]
         L.orc_simd_name.restype = C.c_char_p
         L.orc_max_threads.restype = C.c_int
+        L.orc_set_threads.restype = None
+        L.orc_set_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
@@ -86,3 +88,50 @@ def simd_name() -> str:
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def set_threads(n: int) -> None:
+    """OpenMP thread count of the C oracle (overrides an inherited OMP_NUM_THREADS)."""
+    lib().orc_set_threads(int(n))
+
+
+def blas_flat_search(xb, xq, k, ids=None, tile=1024, threads=None):
+    """faiss exhaustive_inner_product_blas restated [faiss-upstream]: sgemm over (all queries) x (1024 database rows)
+    tiles (numpy -> OpenBLAS), each tile's scores folded into the running top-k (argpartition = the reservoir
+    handler faiss uses for k >= 100).  The n >= 20 branch of knn_inner_product, reached from
+    /root/reference/src/index/feature_search_index.py:113.  Order inside exact ties is NOT the oracle's rule (timing leg)."""
+    from threadpoolctl import threadpool_limits
+    xb = np.ascontiguousarray(xb, np.float32)
+    xq = np.ascontiguousarray(xq, np.float32)
+    n = xq.shape[0]
+    N = xb.shape[0]
+    kk = min(k, N)
+    with threadpool_limits(limits=threads):
+        best_s = np.full((n, kk), -np.inf, np.float32)
+        best_p = np.full((n, kk), -1, np.int64)
+        # faiss merges once per 1024-row tile; numpy's per-call overhead makes that unfair to the CPU, so the
+        # sgemm runs over 16 tiles at a time and the partial top-k is taken once per 16K rows
+        step = tile * 16
+        for j0 in range(0, N, step):
+            j1 = min(N, j0 + step)
+            s = xq @ xb[j0:j1].T
+            m = j1 - j0
+            if m > kk:
+                part = np.argpartition(-s, kk - 1, axis=1)[:, :kk]
+                ps = np.take_along_axis(s, part, axis=1)
+            else:
+                part = np.broadcast_to(np.arange(m), (n, m))
+                ps = s
+            cs = np.concatenate([best_s, ps], axis=1)
+            cp = np.concatenate([best_p, part + j0], axis=1)
+            sel = np.argpartition(-cs, kk - 1, axis=1)[:, :kk]
+            best_s = np.take_along_axis(cs, sel, axis=1)
+            best_p = np.take_along_axis(cp, sel, axis=1)
+        order = np.argsort(-best_s, axis=1, kind="stable")
+        D = np.take_along_axis(best_s, order, axis=1)
+        P = np.take_along_axis(best_p, order, axis=1)
+    I = P if ids is None else np.where(P >= 0, np.asarray(ids)[np.maximum(P, 0)], -1)
+    if kk < k:
+        D = np.concatenate([D, np.full((n, k - kk), np.float32(-3.4028234663852886e38))], axis=1)
+        I = np.concatenate([I, np.full((n, k - kk), -1, np.int64)], axis=1)
+    return D, I

@@ -83,6 +83,16 @@ const char* orc_simd_name(void) {
     return f == ip_avx512 ? "avx512f" : f == ip_avx2 ? "avx2+fma" : "scalar";
 }
 
+/* Thread count for the *_mt / omp-parallel entry points.  torch.distributed.run exports OMP_NUM_THREADS=1 to its
+ * workers; the benchmark's reference arm calls this with the size of its CPU affinity set instead. */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

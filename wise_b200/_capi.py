@@ -55,6 +55,7 @@ SIGNATURES = {
     "wb_ivf_add_preassigned": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),
     "wb_tar_scan": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "wb_tar_read": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, _vp, _vp, C.POINTER(C.c_int64)]),
+    "wb_tf32_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "wb_storage": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "wb_launch_count": (C.c_int64, [_vp]),
     "wb_gemm_stats": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

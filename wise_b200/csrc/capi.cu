@@ -16,6 +16,7 @@
 #include "../../include/wise_b200.h"
 #include "exchange.cuh"
 #include "gemm.cuh"
+#include "gemm_ss.cuh"
 #include "kmeans.cuh"
 #include "merge.cuh"
 #include "scan.cuh"
@@ -97,7 +98,7 @@ struct wb_index {
     bool csr_dirty = true;
     bool contiguous = false;  // rows physically grouped by list (perm is the identity and not stored)
     // scratch
-    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gkeys, gstate, gmargin, eD, eI;
+    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gimg2, gkeys, gstate, gmargin, eD, eI;
     int64_t gemm_launches = 0, gemm_fallbacks = 0;
     // device properties
     int sm_count = 148;
@@ -173,7 +174,7 @@ extern "C" int wb_free(wb_index* h) {
     cudaFree(h->perm);
     cudaFree(h->list_off);
     for (DevBuf* b : {&h->parts, &h->qbuf, &h->dbuf, &h->ibuf, &h->pD, &h->pI, &h->xbuf, &h->idbuf, &h->misc,
-                      &h->kperm, &h->koff, &h->gimg, &h->gkeys, &h->gstate, &h->gmargin, &h->eD, &h->eI})
+                      &h->kperm, &h->koff, &h->gimg, &h->gimg2, &h->gkeys, &h->gstate, &h->gmargin, &h->eD, &h->eI})
         b->release();
     for (int i = 0; i < wb_index::kEvRing; ++i) {
         cudaEventDestroy(h->ev0[i]);
@@ -490,29 +491,41 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     const int kstride = k + cap;
     // measured (10M x 768): 40 / 64 queries 5.9 / 6.3 ms on one CTA vs 6.2 / 6.4 ms on the pair; 128 queries 8.8 vs 8.1 ms
     const bool use2 = BN >= 128 && env_int("WB_GEMM_2CTA", 1) != 0 && (h->sm_count % 2) == 0;
+    // Batches above 128 queries run their filter epochs in 256-query blocks on the SS kernel (gemm_ss.cuh): half as many
+    // passes over the rows and 1.5x fewer L2 bytes per MAC than 128-query blocks.
+    const bool use_f2 = BN >= 128 && filter && use2 && nq > 128 && env_int("WB_GEMM_F2", 1) != 0;
+    const int nqb2 = (int)((nq + kF2BN - 1) / kF2BN);
+    const int nq_pad = use_f2 ? nqb2 * kF2BN : nqb * kGemmBN;  // thresholds / margins of padding queries: +inf / 0
     TRY(h->gimg.ensure((size_t)nqb * nchunks * kGemmBBytes));
     TRY(h->gkeys.ensure((size_t)nq * kstride * sizeof(uint64_t)));
-    TRY(h->gstate.ensure((size_t)nqb * kGemmBN * 4 + (size_t)nq * 4 + 64));
+    TRY(h->gstate.ensure((size_t)nq_pad * 4 + (size_t)nq * 4 + 64));
     float* thr = h->gstate.as<float>();
     float* margin = nullptr;
     if (filter) {
-        TRY(h->gmargin.ensure((size_t)nqb * kGemmBN * 4));
+        TRY(h->gmargin.ensure((size_t)nq_pad * 4));
         margin = h->gmargin.as<float>();
         // |exact - hi.hi| <= 2^-9 |x||q| (two truncations to tf32, Cauchy-Schwarz) + fp32 accumulation slack
         // (n-term fp32 accumulation: <= n * 2^-23 * sum |x_i q_i| even if the tensor core truncates)
         const float c_margin = 1.953125e-3f + (float)ld * 1.1920929e-7f * 1.1f + 1e-5f;
-        const int nqp = nqb * kGemmBN;
-        query_margin_kernel<<<(unsigned)((nqp * 32 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, nqp, ld, h->norm2_max,
-                                                                              c_margin, margin);
+        query_margin_kernel<<<(unsigned)((nq_pad * 32 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, nq_pad, ld, h->norm2_max,
+                                                                                 c_margin, margin);
         CK(cudaGetLastError());
         h->launches++;
     }
-    int* cnt = reinterpret_cast<int*>(thr + (size_t)nqb * kGemmBN);
+    if (use_f2) {
+        TRY(h->gimg2.ensure((size_t)nqb2 * 2 * nchunks * kF2BBytes));
+        const int64_t n4 = (int64_t)nqb2 * 2 * nchunks * 8 * kF2Half;
+        image_queries_f2_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb2,
+                                                                             h->gimg2.as<float>());
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    int* cnt = reinterpret_cast<int*>(thr + (size_t)nq_pad);
     int* overflow = cnt + nq;
     uint64_t* keys = h->gkeys.as<uint64_t>();
     {
-        const int64_t n1 = std::max<int64_t>((int64_t)nqb * kGemmBN, nq * (int64_t)k);
-        init_gemm_state_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(thr, (int)nq, nqb * kGemmBN, cnt, keys, k,
+        const int64_t n1 = std::max<int64_t>((int64_t)nq_pad, nq * (int64_t)k);
+        init_gemm_state_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(thr, (int)nq, nq_pad, cnt, keys, k,
                                                                             kstride, overflow);
         CK(cudaGetLastError());
         const int64_t n2 = (int64_t)nqb * nchunks * 8 * kGemmBN;
@@ -604,8 +617,26 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
         // first epoch: 3xTF32 scores select, the winners are re-scored; later epochs: one-term filter, candidates re-scored
         const bool one_term = filter && r0 > 0;
         c.rescore = filter ? (r0 == 0 ? 2 : 1) : 0;
+        bool launched = false;
+        if constexpr (BN >= 128) {
+            if (use_f2 && one_term) {  // 256-query blocks, both operands from shared memory
+                static thread_local bool a3[64] = {};
+                if (dev >= 64 || !a3[dev]) {
+                    CK(cudaFuncSetAttribute(filter2_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)kF2SmemBytes));
+                    if (dev < 64) a3[dev] = true;
+                }
+                GemmParams g2 = g;
+                g2.nqb = nqb2;
+                g2.bimg = h->gimg2.as<float>();
+                const int64_t ntp = ((r1 - r0 + kGemmBM - 1) / kGemmBM + 1) / 2;
+                const unsigned grid3 = 2u * (unsigned)std::min<int64_t>(ntp * nqb2, h->sm_count / 2);
+                filter2_topk_kernel<false><<<grid3, kF2Threads, kF2SmemBytes, st>>>(tmap, g2);
+                launched = true;
+            }
+        }
         if constexpr (BN >= 128) {  // the CTA pair exists for 128-query blocks only
-            if (use2) {
+            if (use2 && !launched) {
                 static thread_local bool a2[64] = {};
                 if (dev >= 64 || !a2[dev]) {
                     CK(cudaFuncSetAttribute(gemm2_topk_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -620,7 +651,7 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
                 else gemm2_topk_kernel<BN, false><<<grid2, kGemmThreads, Gemm2Cfg<BN>::kSmemBytes, st>>>(tmap, g);
             }
         }
-        if (!use2) {
+        if (!use2 && !launched) {
             if (one_term) gemm_topk_kernel<BN, false, 1><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
             else gemm_topk_kernel<BN, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
         }
@@ -1306,6 +1337,44 @@ extern "C" int wb_ivf_train(wb_index* h, int64_t n, const float* x_host, int nit
     }
     if (e != cudaSuccess) return fail("k-means training failed: %s", cudaGetErrorString(e));
     h->trained = true;
+    return 0;
+}
+
+// ---- TF32 tensor-pipe peak of this GPU, measured with the library's own MMA shape (gemm_ss.cuh) -----------------
+// Denominator for the batched-search roofline in bench.py: `iters` x 4 back-to-back
+// tcgen05.mma.cta_group::2.kind::tf32 (M = 256, N = 256, K = 8) per CTA pair, no loads, best of `reps` launches.
+extern "C" int wb_tf32_peak(int device, int iters, int reps, double* tflops_out, double* ms_out) {
+    if (iters < 1 || reps < 1 || !tflops_out) return fail("bad arguments");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail("no CUDA device available (%s)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail("device %d out of range", device);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("device %d is not sm_100", device);
+    const int npairs = prop.multiProcessorCount / 2;
+    const size_t smem = (size_t)kF2StageBytes + 1024;
+    CK(cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < reps + 1; ++r) {  // first launch is the warm-up
+        CK(cudaEventRecord(e0, 0));
+        tf32_peak_kernel<<<2 * npairs, 128, smem, 0>>>(iters);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flop = (double)npairs * iters * 4.0 * 2.0 * 256.0 * 256.0 * 8.0;
+    *tflops_out = flop / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
     return 0;
 }
 

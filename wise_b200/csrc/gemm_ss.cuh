@@ -1,0 +1,335 @@
+// gemm_ss.cuh - K2 "filter" epochs for large batches: 256-query blocks on a CTA pair, BOTH operands read by the
+// tensor core straight from shared memory (tcgen05.mma.cta_group::2.kind::tf32, SS form, M = 256, N = 256).
+//
+// Same contract as gemm2_topk_kernel<128, false, TERMS = 1> (gemm.cuh): one-term TF32 scores are only a filter, a row
+// becomes a candidate when its score exceeds thr - margin and rescore_candidates_kernel / compact_topk_kernel
+// (merge.cuh) re-score the candidates exactly in fp32, so the result is the exact top-k.  Replaces faiss
+// exhaustive_inner_product_blas [faiss-upstream] reached from /root/reference/src/index/feature_search_index.py:113.
+//
+// Why a second kernel (round 2; profiles/r02/gemm_ss.md): at 256+ queries the TS kernel was bound by L2 -> SM
+// traffic, not by its hand-offs: every (row tile, 128-query block) item pulls 16 KB of rows + 8 KB of query image per
+// 32-float chunk for 0.5 M MACs per SM (24 KB x 148 SMs per ~600 cycles = the ~6300 B/cycle the L2 slices deliver).
+// kind::tf32 reads fp32 words and uses their top 19 bits, so the one-term operand needs NO transform at all:
+//   * the raw fp32 row tile lands by 2-D TMA (SWIZZLE_128B) and IS the A operand (K-major SW128 descriptor);
+//   * N = 256 queries per instruction: 16 KB rows + 16 KB image per chunk for 1 M MACs per SM - 1.5x fewer bytes per MAC,
+//     and half as many passes over the rows;
+//   * no transform warps, no tcgen05.st, no A slots in tensor memory: TMEM holds two 256-column accumulators, so the
+//     epilogue of one tile still overlaps the MMAs of the next.
+// Roles (12 warps): warp 0 producer (TMA rows + bulk copy of this CTA's half image, one barrier per stage),
+// warp 1 MMA issuer (leader) / "my stage landed" forwarder (peer), warp 2 TMEM allocator, warps 4-11 epilogue
+// (TMEM lane quarter = warp & 3, column half = (warp - 4) >> 2).
+#pragma once
+#include "gemm.cuh"
+
+namespace wb {
+
+constexpr int kF2Half = 128;                      // queries per CTA; the pair's block is 256
+constexpr int kF2BN = 2 * kF2Half;
+constexpr int kF2BBytes = kF2Half * kGemmBK * 4;  // 16 KB: 128 queries x 32 floats, no-swizzle core-matrix layout
+constexpr int kF2StageBytes = kGemmABytes + kF2BBytes;
+constexpr int kF2Stages = 6;
+constexpr int kF2Threads = 384;
+constexpr int kF2EpiThreads = 256;
+constexpr int kF2NumBars = 3 * kF2Stages + 4;
+constexpr size_t kF2SmemBytes = 1024 + (size_t)kF2Stages * kF2StageBytes + kF2NumBars * 8 + 16 + 2 * kF2BN * 4;
+static_assert(kF2SmemBytes <= 232448, "shared memory budget");
+
+// Query image of the SS kernel: image[qb][half][chunk][k16 = 0..7][n = 0..127][4 floats] - raw fp32 (the tensor core
+// uses the tf32 part), K-major core matrices: 8 queries x 16 B are 128 contiguous bytes, SBO = 128 B between
+// 8-query groups, LBO = 128 * 16 B between 16-byte k columns.
+__global__ void image_queries_f2_kernel(const float* q, int nq, int ld, int nchunks, int nqb, float* img) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one float4 per thread
+    const int64_t total = (int64_t)nqb * 2 * nchunks * 8 * kF2Half;
+    if (i >= total) return;
+    const int n = (int)(i % kF2Half);
+    const int k16 = (int)((i / kF2Half) % 8);
+    const int chunk = (int)((i / (kF2Half * 8)) % nchunks);
+    const int half = (int)((i / ((int64_t)kF2Half * 8 * nchunks)) % 2);
+    const int qb = (int)(i / ((int64_t)kF2Half * 8 * nchunks * 2));
+    const int qi = qb * kF2BN + half * kF2Half + n;
+    const int col = chunk * kGemmBK + k16 * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qi < nq) {
+        const float* src = q + (size_t)qi * ld + col;
+        if (col + 3 < ld) v = *reinterpret_cast<const float4*>(src);  // ld is a multiple of 4
+    }
+    reinterpret_cast<float4*>(img)[i] = v;
+}
+
+__device__ __forceinline__ void umma_tf32_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+
+// K-major SWIZZLE_128B operand (what a 2-D TMA load with CU_TENSOR_MAP_SWIZZLE_128B of 32-float rows produces):
+// 8-row groups are 1024 B apart (SBO), LBO is unused (1), layout type 2, descriptor version 1.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+template <bool TIMING_ONLY = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF2Threads, 1)
+filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_f2[];
+    unsigned char* stages = smem_f2 + ((1024u - (smem_u32(smem_f2) & 1023u)) & 1023u);  // same offset in both CTAs
+    uint64_t* full = reinterpret_cast<uint64_t*>(stages + (size_t)kF2Stages * kF2StageBytes);  // my rows + my half image landed
+    uint64_t* peer_full = full + kF2Stages;   // leader only: the peer's stage landed
+    uint64_t* empty = peer_full + kF2Stages;  // both: the MMAs that read this stage have retired (multicast commit)
+    uint64_t* d_full = empty + kF2Stages;     // both: accumulator ready (multicast commit)
+    uint64_t* d_empty = d_full + 2;           // leader only: both epilogues drained the accumulator (16 warp arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+    float* thr_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256], 16-byte aligned
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int64_t ntiles = (p.row_end - p.row_begin + kGemmBM - 1) / kGemmBM;
+    const int64_t ntp = (ntiles + 1) / 2;  // tile pairs
+    const int64_t nwork = ntp * p.nqb;
+    const int64_t my_work = nwork > pair ? (nwork - pair + npairs - 1) / npairs : 0;
+    // (tile pair, query block) items are interleaved over the pairs: neighbouring pairs work on the same rows with
+    // different query blocks at the same time, so only the first of them misses L2
+    auto work_at = [&](int64_t it, int64_t& tile, int& qb) {  // tile = THIS CTA's row tile
+        const int64_t w = pair + it * npairs;
+        const int64_t tp = w / p.nqb;
+        qb = (int)(w - tp * p.nqb);
+        tile = 2 * tp + crank;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < kF2Stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&peer_full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&d_full[b], 1);
+            mbar_init(&d_empty[b], 16);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== producer: rows (2-D TMA) + this CTA's half image ============
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t it = 0; it < my_work; ++it) {
+            int64_t tile;
+            int qb;
+            work_at(it, tile, qb);
+            const int row0 = (int)(p.row_begin + tile * kGemmBM);  // may be past row_end: TMA zero-fills
+            const float* bsrc = p.bimg + (size_t)(2 * qb + (int)crank) * p.nchunks * (kF2BBytes / 4);
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait(&empty[s], ph ^ 1u);
+                if (elect_one_sync()) {
+                    unsigned char* st = stages + (size_t)s * kF2StageBytes;
+                    mbar_arrive_expect_tx(&full[s], kF2StageBytes);
+                    tma_load_2d(st, &tmap, c * kGemmBK, row0, &full[s]);
+                    bulk_g2s(st + kGemmABytes, bsrc + (size_t)c * (kF2BBytes / 4), kF2BBytes, &full[s]);
+                }
+                __syncwarp();
+                if (++s == kF2Stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1 && !leader) {
+        // =============================== peer: tell the leader when my stage has landed ==============
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t it = 0; it < my_work; ++it) {
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait(&full[s], ph);
+                if (elect_one_sync()) mbar_arrive_cluster(&peer_full[s], 0);
+                __syncwarp();
+                if (++s == kF2Stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== leader: MMA issuer for the pair =============================
+        constexpr uint32_t idesc = umma_idesc_tf32(2 * kGemmBM, kF2BN);
+        const uint64_t adesc0 = umma_smem_desc_sw128(smem_u32(stages));
+        const uint64_t bdesc0 = umma_smem_desc(smem_u32(stages + kGemmABytes), kF2Half * 16, 128);
+        const uint32_t a_lo0 = (uint32_t)adesc0, a_hi = (uint32_t)(adesc0 >> 32);
+        const uint32_t b_lo0 = (uint32_t)bdesc0, b_hi = (uint32_t)(bdesc0 >> 32);
+        int s = 0;
+        uint32_t ph = 0;
+        int buf = 0;
+        uint32_t dph = 0;
+        for (int64_t it = 0; it < my_work; ++it) {
+            mbar_wait(&d_empty[buf], dph ^ 1u);  // both epilogues have drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kF2BN);
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait(&full[s], ph);
+                mbar_wait(&peer_full[s], ph);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t so = (uint32_t)s * (uint32_t)(kF2StageBytes >> 4);
+#pragma unroll
+                    for (int j = 0; j < kGemmBK / 8; ++j) {
+                        // one k-step = 8 tf32 = 32 B: inside the 128-byte swizzle atom for A, two 16-byte k columns for B
+                        const uint64_t da = desc_from_words(a_lo0 + so + (uint32_t)(j * 2), a_hi);
+                        const uint64_t db = desc_from_words(b_lo0 + so + (uint32_t)((j * 2 * kF2Half * 16) >> 4), b_hi);
+                        umma_tf32_ss_2cta(d_tmem, da, db, idesc, (c | j) != 0);
+                    }
+                    umma_commit_2cta(&empty[s]);
+                    if (c == p.nchunks - 1) umma_commit_2cta(&d_full[buf]);
+                }
+                __syncwarp();
+                if (++s == kF2Stages) { s = 0; ph ^= 1u; }
+            }
+            if (++buf == 2) { buf = 0; dph ^= 1u; }
+        }
+    } else if (warp >= 4) {
+        // =============================== epilogue (this CTA's 128 rows x 256 queries) ================
+        const int quarter = warp & 3;
+        const int chalf = (warp - 4) >> 2;  // which 128 of the 256 query columns
+        const int etid = tid - 4 * 32;      // 0..255
+        int buf = 0;
+        uint32_t dph = 0;
+        for (int64_t it = 0; it < my_work; ++it) {
+            int64_t tile;
+            int qb;
+            work_at(it, tile, qb);
+            const int64_t row = p.row_begin + tile * kGemmBM + quarter * 32 + lane;
+            const bool row_ok = row < p.row_end;
+            thr_s[buf * kF2BN + etid] = p.thr[qb * kF2BN + etid] - p.margin[qb * kF2BN + etid];  // +inf for padding
+            named_bar_sync(kBarEpilogue, kF2EpiThreads);
+            mbar_wait(&d_full[buf], dph);
+            tc_fence_after();
+            const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kF2BN + chalf * kF2Half);
+            const float* thr_w = thr_s + buf * kF2BN + chalf * kF2Half;
+#pragma unroll 1
+            for (int cb = 0; cb < kF2Half / 32; ++cb) {
+                uint32_t v[32];
+                tmem_ld32(td + cb * 32, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if constexpr (TIMING_ONLY) continue;
+                // almost nothing passes: one vote per 32 columns, the per-column path only when something did
+                bool any = false;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 t = *reinterpret_cast<const float4*>(thr_w + cb * 32 + j4 * 4);
+                    any |= __uint_as_float(v[j4 * 4 + 0]) > t.x;
+                    any |= __uint_as_float(v[j4 * 4 + 1]) > t.y;
+                    any |= __uint_as_float(v[j4 * 4 + 2]) > t.z;
+                    any |= __uint_as_float(v[j4 * 4 + 3]) > t.w;
+                }
+                if (!__any_sync(0xffffffffu, any && row_ok)) continue;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float sc = __uint_as_float(v[j]);
+                    const bool pass = row_ok && sc > thr_w[cb * 32 + j];
+                    const unsigned m = __ballot_sync(0xffffffffu, pass);
+                    if (m) {
+                        const int qi = qb * kF2BN + chalf * kF2Half + cb * 32 + j;  // < nq: padded queries have thr = +inf
+                        int base = 0;
+                        if (lane == (__ffs(m) - 1)) base = atomicAdd(&p.cnt[qi], __popc(m));
+                        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                        if (pass) {
+                            const int slot = base + __popc(m & ((1u << lane) - 1));
+                            if (slot < p.cap) p.keys[(size_t)qi * p.kstride + p.k + slot] = make_key(sc, (uint32_t)row);
+                            else *p.overflow = 1;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&d_empty[buf], 0);
+            named_bar_sync(kBarEpilogue, kF2EpiThreads);  // thr_s[buf] may be rewritten two tiles later
+            if (++buf == 2) { buf = 0; dph ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's shared memory and TMEM stay alive until the leader's last MMA has retired
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+// ---- TF32 tensor-pipe peak, measured with this library's own instruction shape ------------------------------------
+// Every CTA pair issues `iters` x 4 back-to-back tcgen05.mma.cta_group::2.kind::tf32 (M = 256, N = 256, K = 8, both
+// operands from shared memory - whatever bytes are there; tf32 arithmetic does not care) into two alternating
+// accumulators and waits for the last commit.  No loads, no epilogue: this is the ceiling filter2_topk_kernel's
+// MMA stream could reach, and the denominator bench.py reports batch-1024 throughput against.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
+    extern __shared__ __align__(1024) unsigned char smem_pk[];
+    unsigned char* st = smem_pk + ((1024u - (smem_u32(smem_pk) & 1023u)) & 1023u);
+    __shared__ uint64_t done_bar;
+    __shared__ uint32_t tmem_slot_pk;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const bool leader = cluster_ctarank() == 0;
+    for (int i = tid; i < kF2StageBytes / 4; i += blockDim.x) reinterpret_cast<float*>(st)[i] = 1.0f;
+    if (tid == 0) {
+        mbar_init(&done_bar, 1);
+        fence_mbar_init();
+    }
+    fence_proxy_async();
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot_pk)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot_pk;
+    if (warp == 1 && leader) {
+        constexpr uint32_t idesc = umma_idesc_tf32(2 * kGemmBM, kF2BN);
+        const uint64_t adesc0 = umma_smem_desc_sw128(smem_u32(st));
+        const uint64_t bdesc0 = umma_smem_desc(smem_u32(st + kGemmABytes), kF2Half * 16, 128);
+        const uint32_t a_lo0 = (uint32_t)adesc0, a_hi = (uint32_t)(adesc0 >> 32);
+        const uint32_t b_lo0 = (uint32_t)bdesc0, b_hi = (uint32_t)(bdesc0 >> 32);
+        for (int it = 0; it < iters; ++it) {
+            if (elect_one_sync()) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)((it & 1) * kF2BN);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t da = desc_from_words(a_lo0 + (uint32_t)(j * 2), a_hi);
+                    const uint64_t db = desc_from_words(b_lo0 + (uint32_t)((j * 2 * kF2Half * 16) >> 4), b_hi);
+                    umma_tf32_ss_2cta(d_tmem, da, db, idesc, j != 0);
+                }
+                if (it == iters - 1) umma_commit_2cta(&done_bar);
+            }
+            __syncwarp();
+        }
+    }
+    if (warp == 1) {
+        mbar_wait(&done_bar, 0);  // the commit is multicast to both CTAs
+        tc_fence_after();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+}  // namespace wb
