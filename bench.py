@@ -12,18 +12,27 @@ reference serves, /root/reference/api/routes.py:1407) over the whole database:
            the queries and D2H of (D, I) inside the timed region
   roofline achieved = N*d*4 bytes / scan-kernel duration (events inside the library, same stream)
            vs the measured copy bandwidth in MEASURED_PEAKS.json
+  parity_check  the (D, I) of the LAST timed step verified after the timed region on every rank against an fp64
+           pass over the regenerated rows (torch, chunked): returned scores within 1e-5, no row outside the
+           result beats the k-th score beyond the 4e-6 near-tie band, all ranks returned identical bytes, and a
+           planted exact duplicate (last row == row 0, on different ranks when N > 1) ties in insertion order
+  secondary (N = 1) the same measurement at batch 16 (K2, HBM roofline) and batch 1024 (K2 256-query blocks,
+           tensor roofline against the TF32 peak measured live with the library's own MMA shape), each with its own
+           parity_check; batch 1024 also carries the BLAS-path CPU baseline
   cpu_baseline  the faiss-equivalent C restatement (oracle/cpu_flat.c) on this box's host cores,
            on a bounded row sample, scaled linearly (faiss itself is not installable: BASELINE.md 3)
-N > 1: the 10M rows are split into N contiguous shards (strong scaling), one process per GPU, one
-NCCL all-gather of the k candidates per step, K3 merge on every rank.
-`--impl reference` times the CPU restatement with all host threads (rank 0 only).
+N > 1: the 10M rows are split into N contiguous shards (strong scaling), one process per GPU; the exchange of
+the k candidates per query is the library's own NVLink peer-memory kernel (exchange.cuh), NCCL carries only the
+benchmark's barriers and reductions.
+`--impl reference` times the CPU restatement with all host threads (rank 0 only), on the full 10M x 768 matrix
+when host memory allows.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -35,6 +44,10 @@ import numpy as np  # noqa: E402
 
 METRIC = "QPS, IndexFlatIP top-100 (10Mx768 fp32)"
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+GEN_CHUNK = 250_000        # rows per generator chunk (global grid: the same rows whatever the sharding)
+NCENTRES = 4096
+SCORE_TOL = 1e-5           # BASELINE.json north_star
+TIE_BAND = 4e-6            # near-tie band of the parity contract
 
 
 def parse():
@@ -49,21 +62,83 @@ def parse():
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--sweep", default="", help="comma list of extra batch sizes to report, e.g. 2,4,8")
+    ap.add_argument("--secondary", default="auto", help="comma list of extra batch sizes measured WITH roofline and "
+                    "parity_check (default: 16,1024 on one GPU at batch 1; 'none' to skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--mixed", action="store_true",
                     help="config 5: half of the batch are 'combined' queries normalise(2.0*t + 1.0*i - 0.2*n) "
                          "(/root/reference/api/routes.py:759-850)")
     return ap.parse_args()
 
 
-def workload_name(a):
-    return f"IndexFlatIP top-{a.k} over {a.rows}x{a.dim} fp32, query batch {a.batch}" + (" (mixed text/combined)" if a.mixed else "")
+def workload_name(a, batch=None):
+    b = a.batch if batch is None else batch
+    return f"IndexFlatIP top-{a.k} over {a.rows}x{a.dim} fp32, query batch {b}" + (" (mixed text/combined)" if a.mixed else "")
+
+
+def config_of(a, batch=None):
+    """Identical on both arms (ours / reference) for the same command line."""
+    return {"workload": workload_name(a, batch), "rows": a.rows, "dim": a.dim, "k": a.k,
+            "batch": a.batch if batch is None else batch,
+            "generator": f"clustered unit vectors, {NCENTRES} centres, noise 0.6 (SURVEY.md 8d)",
+            "l2": "database (>= 3.8 GB per GPU) is far larger than the 126 MB L2; no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------------
 # synthetic "CLIP-like" data (SURVEY.md 8d): rows = normalise(c_j + 0.6 g), generated on the device
 # ------------------------------------------------------------------------------------------------
-def fill_index_clustered(index, lo, hi, d, seed, device, chunk=500_000, ncentres=4096):
+class RowSource:
+    """Global rows [0, rows) on a fixed chunk grid, chunk c seeded by (seed, c): any rank can regenerate any
+    row.  The LAST row is an exact copy of row 0 (the planted duplicate of the parity check)."""
+
+    def __init__(self, rows, d, seed, device, ncentres=NCENTRES):
+        import torch
+        self.rows, self.d, self.seed, self.device = rows, d, seed, device
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        self.centres = torch.nn.functional.normalize(torch.randn(ncentres, d, device=device, generator=gen), dim=1)
+        self._row0 = None
+
+    def _chunk(self, c):
+        import torch
+        s, e = c * GEN_CHUNK, min(self.rows, (c + 1) * GEN_CHUNK)
+        g2 = torch.Generator(device=self.device)
+        g2.manual_seed(self.seed * 1_000_003 + c)
+        j = torch.randint(0, self.centres.shape[0], (e - s,), device=self.device, generator=g2)
+        x = self.centres[j] + 0.6 * torch.randn(e - s, self.d, device=self.device, generator=g2) / (self.d ** 0.5)
+        return torch.nn.functional.normalize(x, dim=1)
+
+    def row0(self):
+        if self._row0 is None:
+            self._row0 = self._chunk(0)[0].clone()
+        return self._row0
+
+    def chunks(self, lo, hi):
+        """Yield (s, e, x[e-s, d]) covering [lo, hi) in grid order."""
+        for c in range(lo // GEN_CHUNK, (hi + GEN_CHUNK - 1) // GEN_CHUNK):
+            cs, ce = c * GEN_CHUNK, min(self.rows, (c + 1) * GEN_CHUNK)
+            x = self._chunk(c)
+            if ce == self.rows and self.rows > 1:
+                x[-1] = self.row0()  # planted duplicate
+            s, e = max(cs, lo), min(ce, hi)
+            yield s, e, x[s - cs:e - cs].contiguous()
+
+
+def fill_index(index, src, lo, hi):
+    import torch
+    from wise_b200 import _capi
+    L = _capi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    index.reserve(hi - lo)
+    for s, e, x in src.chunks(lo, hi):
+        ids = torch.arange(s, e, dtype=torch.int64, device=src.device)
+        _capi.check(L.wb_add_with_ids_dev(index._h, e - s, x.data_ptr(), ids.data_ptr(), st))
+        torch.cuda.synchronize()
+
+
+def fill_index_clustered(index, lo, hi, d, seed, device, chunk=500_000, ncentres=NCENTRES):
+    """Older helper kept for scripts/: rows [lo, hi) of a clustered store (chunks addressed by their start row)."""
     import torch
     from wise_b200 import _capi
     L = _capi.lib()
@@ -76,7 +151,7 @@ def fill_index_clustered(index, lo, hi, d, seed, device, chunk=500_000, ncentres
     for s in range(lo, hi, chunk):
         e = min(hi, s + chunk)
         g2 = torch.Generator(device=device)
-        g2.manual_seed(seed * 1_000_003 + s)  # chunk-addressed: same rows whatever the sharding
+        g2.manual_seed(seed * 1_000_003 + s)
         j = torch.randint(0, ncentres, (e - s,), device=device, generator=g2)
         x = centres[j] + 0.6 * torch.randn(e - s, d, device=device, generator=g2) / (d ** 0.5)
         x = torch.nn.functional.normalize(x, dim=1).contiguous()
@@ -164,9 +239,25 @@ def cpu_info():
     return {"model": model, "cpu_count": os.cpu_count(), "affinity": len(os.sched_getaffinity(0))}
 
 
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
+
+
+def host_threads():
+    """All the host threads this process may use (torch.distributed.run exports OMP_NUM_THREADS=1: ignored)."""
+    return max(1, len(os.sched_getaffinity(0)))
+
+
 def cpu_restatement(sample_rows, q, k, n_full, mt, reps=3):
     """Time oracle/cpu_flat.c (faiss-equivalent restatement) on `sample_rows`, scale to n_full rows."""
     from oracle import cpu as OC
+    OC.set_threads(host_threads())
     OC.flat_search(sample_rows[:1000], q, k, mt=mt)  # warm-up (thread pool, page-in)
     ts = []
     for _ in range(reps):
@@ -178,36 +269,142 @@ def cpu_restatement(sample_rows, q, k, n_full, mt, reps=3):
     return q.shape[0] / (t_med * scale), t_med, (OC.max_threads() if mt else min(q.shape[0], OC.max_threads())), OC.simd_name()
 
 
+def cpu_blas(sample_rows, q, k, n_full, reps=3):
+    """faiss's n >= 20 path restated: OpenBLAS sgemm tiles + partial selection (oracle/cpu.py blas_flat_search)."""
+    from oracle import cpu as OC
+    th = host_threads()
+    OC.blas_flat_search(sample_rows[:20000], q, k, threads=th)
+    ts = []
+    for _ in range(reps):
+        t = time.perf_counter()
+        OC.blas_flat_search(sample_rows, q, k, threads=th)
+        ts.append(time.perf_counter() - t)
+    t_med = float(np.median(ts))
+    scale = n_full / sample_rows.shape[0]
+    return q.shape[0] / (t_med * scale), t_med, th
+
+
 # ------------------------------------------------------------------------------------------------
+def gen_clustered_host(n, d, seed, threads):
+    """oracle.clustered_unit's distribution, generated chunk-parallel (numpy releases the GIL in the RNG)."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(seed)
+    centres = rng.standard_normal((NCENTRES, d), dtype=np.float32)
+    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+    x = np.empty((n, d), np.float32)
+    step = 100_000
+
+    def work(s):
+        e = min(n, s + step)
+        r = np.random.default_rng(seed * 1_000_003 + s)
+        j = r.integers(0, NCENTRES, size=e - s)
+        g = r.standard_normal((e - s, d), dtype=np.float32)
+        g *= np.float32(0.6 / np.sqrt(d))
+        g += centres[j]
+        g /= np.linalg.norm(g, axis=1, keepdims=True)
+        x[s:e] = g
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, range(0, n, step)))
+    return centres, x
+
+
 def run_reference(a):
-    """--impl reference: the reference's CPU path (faiss-equivalent restatement; faiss is absent),
-    all host threads, bounded sample.  Rank 0 only."""
+    """--impl reference: the reference's CPU path (faiss-equivalent restatement; faiss is absent), all host
+    threads.  Rank 0 only.  Full 10M x 768 when host memory allows, else a bounded sample scaled linearly."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle import oracle as O
-    n_s = min(a.cpu_sample_rows, a.rows)
-    xb = O.clustered_unit(n_s, a.dim, 4096, 2024)
-    q = O.clustered_unit(a.batch, a.dim, 4096, 2025)
     from oracle import cpu as OC
-    OC.flat_search(xb[:1000], q, a.k, mt=True)
+    th = host_threads()
+    OC.set_threads(th)
+    need = a.rows * a.dim * 4
+    avail = mem_available_bytes()
+    n_s = a.rows if avail > need + (12 << 30) else min(a.cpu_sample_rows, a.rows)
+    if os.environ.get("WB_REF_ROWS"):
+        n_s = min(a.rows, int(os.environ["WB_REF_ROWS"]))
+    t0 = time.perf_counter()
+    centres, xb = gen_clustered_host(n_s, a.dim, 2024, th)
+    rq = np.random.default_rng(2025)
+    q = centres[rq.integers(0, NCENTRES, size=a.batch)] + np.float32(0.6 / np.sqrt(a.dim)) * rq.standard_normal((a.batch, a.dim), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q = np.ascontiguousarray(q, np.float32)
+    t_gen = time.perf_counter() - t0
+    use_blas = a.batch >= 20  # faiss: knn_inner_product switches to the BLAS path at 20 queries [faiss-upstream]
+
+    def step():
+        if use_blas:
+            return OC.blas_flat_search(xb, q, a.k, threads=th)
+        return OC.flat_search(xb, q, a.k, mt=True)
+
+    OC.flat_search(xb[:1000], q[:1], a.k, mt=True)
     for _ in range(a.warmup):
-        OC.flat_search(xb, q, a.k, mt=True)
+        step()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        OC.flat_search(xb, q, a.k, mt=True)
+        step()
     dt = time.perf_counter() - t0
     scale = a.rows / n_s
     ms_step = dt / a.steps * 1e3 * scale
     qps = a.batch / (ms_step / 1e3)
-    sample = (f"{n_s} of {a.rows} rows per step (time scaled x{scale:g}); oracle/cpu_flat.c orc_flat_search_mt, "
-              f"{OC.simd_name()}, {OC.max_threads()} threads; faiss itself is not installable here")
+    fn = "oracle/cpu.py blas_flat_search (OpenBLAS sgemm tiles + argpartition)" if use_blas else \
+        f"oracle/cpu_flat.c orc_flat_search_mt ({OC.simd_name()}, database split over the threads)"
+    sample = (("the full matrix" if n_s == a.rows else f"{n_s} of {a.rows} rows per step (time scaled x{scale:g})") +
+              f"; {fn}; {th} threads; generated in {t_gen:.1f} s; faiss itself is not installable here")
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a), "host": cpu_info()},
-            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": OC.max_threads(), "kind": "port", "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": config_of(a), "host": cpu_info(),
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": th, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def parity_check(src, lo, hi, q, D, I, k, world, device):
+    """Verify (D, I) = global top-k of queries q (all [*, .] device tensors, identical on every rank) against an fp64
+    pass over THIS rank's regenerated rows; partial counts are summed over the ranks.  Returns a dict (rank-identical)."""
+    import torch
+    import torch.distributed as dist
+    nq = q.shape[0]
+    q64 = q.double()
+    D64 = D.double()
+    kth = D64[:, k - 1]                              # k-th returned score per query
+    above = torch.zeros(nq, dtype=torch.int64, device=device)        # rows whose exact score beats kth + band
+    ret_above = torch.zeros(nq, dtype=torch.int64, device=device)    # ... of which are in the returned list
+    found = torch.zeros(nq, dtype=torch.int64, device=device)        # returned ids located in my shard
+    max_err = torch.zeros(1, dtype=torch.float64, device=device)
+    rows_checked = 0
+    qcols = torch.arange(nq, device=device).unsqueeze(1).expand(nq, k)
+    for s, e, x in src.chunks(lo, hi):
+        s64 = x.double() @ q64.T                     # [m, nq] exact scores (fp64 accumulate of the fp32 inputs)
+        above += (s64 > (kth + TIE_BAND).unsqueeze(0)).sum(dim=0)
+        m = (I >= s) & (I < e)
+        if bool(m.any()):
+            ri, qi = (I[m] - s), qcols[m]
+            ex = s64[ri, qi]
+            max_err = torch.maximum(max_err, (ex - D64[m]).abs().max().reshape(1))
+            ret_above.index_add_(0, qi, (ex > kth[qi] + TIE_BAND).long())
+            found.index_add_(0, qi, torch.ones_like(qi))
+        rows_checked += e - s
+        del s64
+    t_rows = torch.tensor([rows_checked], dtype=torch.int64, device=device)
+    ident = True
+    if world > 1:
+        for t in (above, ret_above, found, t_rows):
+            dist.all_reduce(t)
+        dist.all_reduce(max_err, op=dist.ReduceOp.MAX)
+        for t in (I, D.view(torch.int32)):
+            mx, mn = t.clone(), t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            ident = ident and bool((mx == mn).all())
+    sorted_ok = bool((D[:, 1:] <= D[:, :-1]).all())
+    uniq_ok = all(int(torch.unique(I[j]).numel()) == k for j in range(min(nq, 64)))
+    violations = int((above - ret_above).clamp(min=0).sum()) + int((found != k).sum())
+    return {"rows_checked": int(t_rows.item()), "queries": nq, "max_abs_err": float(max_err.item()),
+            "violations": violations, "sorted": sorted_ok, "unique_ids": uniq_ok, "ranks_identical": ident,
+            "score_tol": SCORE_TOL, "tie_band": TIE_BAND,
+            "ok": bool(violations == 0 and float(max_err.item()) <= SCORE_TOL and sorted_ok and uniq_ok and ident)}
 
 
 def run_ours(a):
@@ -232,8 +429,10 @@ def run_ours(a):
     L = _capi.lib()
 
     lo, hi = shard_range(a.rows, rank, world)
+    src = RowSource(a.rows, a.dim, 2024, device)
+    centres = src.centres
     index = faiss.IndexIDMap(faiss.IndexFlatIP(a.dim, device=local_rank))
-    centres, first_rows = fill_index_clustered(index, lo, hi, a.dim, 2024, device)
+    fill_index(index, src, lo, hi)
     assert index.ntotal == hi - lo
     sharded = ShardedIndex(index)
     L.wb_set_timing(index._h, 1)
@@ -244,7 +443,8 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     def timed_steps(nq, steps, warmup):
-        """Device-resident queries; returns (ms per step [max over ranks], scan-kernel ms per step, launches)."""
+        """Device-resident queries; returns (ms per step [max over ranks], scan-kernel ms per step, launches,
+        queries of the last step, its D, its I)."""
         qs = make_queries(centres, nq * (steps + warmup), a.dim, 2025, device).view(steps + warmup, nq, a.dim)
         for i in range(warmup):
             sharded.search_dev(qs[i], a.k)
@@ -253,21 +453,20 @@ def run_ours(a):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for i in range(steps):
-            sharded.search_dev(qs[warmup + i], a.k)
+            D, I = sharded.search_dev(qs[warmup + i], a.k)
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1) / steps
-        launches = L.wb_launch_count(index._h) - l0 + (steps if world > 1 else 0)  # + K3 merge of the gathered parts
+        launches = L.wb_launch_count(index._h) - l0 + (steps if world > 1 else 0)  # + the exchange kernel per step
         # per-launch scan durations OF THE TIMED REGION: event pairs recorded by the library around the
-        # scan kernel on the launching stream (ring of 128), read back after the region has ended
-        import ctypes
+        # scan kernel(s) on the launching stream (ring of 128), read back after the region has ended
         buf = (ctypes.c_float * 128)()
         n = L.wb_scan_ms_history(index._h, buf, min(steps, 128))
         scan_ms = [buf[i] for i in range(n)]
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), float(np.mean(scan_ms)), int(launches)
+        return float(t.item()), float(np.mean(scan_ms)), int(launches), qs[steps + warmup - 1], D, I
 
     def timed_e2e(nq, steps, warmup):
         """Public API, pinned host buffers in, numpy out; wall clock around synchronous calls."""
@@ -287,92 +486,152 @@ def run_ours(a):
         t = torch.tensor([dt], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) * 1e3, D, I
+        return float(t.item()) * 1e3, q_all[steps + warmup - 1], D, I
+
+    def preroll(nq):
+        """Untimed, all ranks: keep the GPU under the same load for ~0.6 s so that the clock samples bracket the
+        timed region (the number of searches must be the same on every rank: the exchange is a collective)."""
+        qpre = make_queries(centres, nq, a.dim, 2024, device)
+        barrier()
+        t_pre = time.perf_counter()
+        for _ in range(3):
+            sharded.search_dev(qpre, a.k)
+        torch.cuda.synchronize()
+        t3 = torch.tensor([(time.perf_counter() - t_pre) / 3], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        for _ in range(int(min(2000, max(1, 0.6 / max(float(t3.item()), 1e-5))))):
+            sharded.search_dev(qpre, a.k)
+        torch.cuda.synchronize()
+
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        peaks = json.load(open(peaks_file))
+        peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peaks, peak, peak_src = {}, HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+    local_bytes = (hi - lo) * a.dim * 4
+    tf32_peak = {}
+
+    def measure_tf32_peak():
+        """TF32 tensor peak of THIS GPU with the library's own MMA shape: burst (one 5 ms launch) and sustained
+        (~2 s back to back, second half timed: the power cap has settled)."""
+        if not tf32_peak:
+            tb, ts = ctypes.c_double(), ctypes.c_double()
+            _capi.check(L.wb_tf32_peak(local_rank, 20000, 400, ctypes.byref(tb), ctypes.byref(ts)))
+            tf32_peak.update({"burst": tb.value, "sustained": ts.value})
+        return tf32_peak
+
+    def roofline_of(batch, scan_ms):
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf):
+            for t in json.load(open(tf)).get("captures", []):
+                if t.get("rows") == hi - lo and t.get("dim") == a.dim and t.get("batch") == batch:
+                    traffic = t.get("dram_bytes_per_launch")
+        if batch < 5:   # K1: CUDA-core scan, HBM-bound; one pass of the row store per <= 8 queries
+            passes = (batch + 7) // 8
+            achieved = local_bytes * passes / (scan_ms * 1e-3) / 1e9
+            return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "kernel": "scan_topk_kernel", "bytes_per_launch": local_bytes,
+                    "launch_ms": scan_ms / passes, "peak_source": peak_src}
+        if batch <= 128:  # K2, one query block: ONE pass over the rows per search -> HBM is the roofline
+            achieved = local_bytes / (scan_ms * 1e-3) / 1e9
+            return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "kernel": "gemm_topk_kernel (all epochs of a search, compactions included)",
+                    "bytes_per_launch": local_bytes, "launch_ms": scan_ms, "peak_source": peak_src,
+                    "note": "tcgen05 TF32 filter epochs + exact fp32 re-scoring of the candidates"}
+        # K2 in 256-query blocks: tensor pipe; all epochs of a search timed together
+        flop = 2.0 * batch * (hi - lo) * a.dim
+        achieved = flop / (scan_ms * 1e-3) / 1e12
+        pk = measure_tf32_peak()
+        return {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["sustained"], "traffic": traffic,
+                "kernel": "filter2_topk_kernel (all epochs of a search: 3xTF32 first epoch, one-term 256-query filter "
+                          "epochs, exact fp32 re-scoring, compactions)",
+                "flop_per_search": flop, "search_ms": scan_ms, "peak_burst": pk["burst"],
+                "frac_of_burst": achieved / pk["burst"],
+                "frac_of_bf16_sustained_half": (achieved / (float(peaks["bf16_tflops_sustained"]) / 2.0)
+                                                if "bf16_tflops_sustained" in peaks else None),
+                "peak_source": "wb_tf32_peak measured in this run on this GPU: back-to-back tcgen05.mma.cta_group::2."
+                               "kind::tf32 M=256 N=256 K=8, no loads; sustained = 2nd half of 400 x 5 ms launches "
+                               "(power cap settled), burst = best single launch",
+                "note": "algorithmic flops 2*B*N*d; the filter epochs issue each flop once (one-term TF32)"}
+
+    def dup_tie_check():
+        """The planted duplicate: query = row 0 exactly; rows 0 and rows-1 hold the same vector (on different ranks when
+        N > 1), so they tie bit for bit and must come back in insertion order."""
+        qd = src.row0().view(1, a.dim).contiguous()
+        D, I = sharded.search_dev(qd, a.k)
+        torch.cuda.synchronize()
+        Dh, Ih = D[0].cpu().numpy(), I[0].cpu().numpy()
+        return {"ids": [int(Ih[0]), int(Ih[1])], "scores_equal_bits": bool(Dh[0].tobytes() == Dh[1].tobytes()),
+                "ok": bool(Ih[0] == 0 and Ih[1] == a.rows - 1 and Dh[0].tobytes() == Dh[1].tobytes())}
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    # pre-roll (untimed, all ranks): keep the GPU under the same load for ~0.6 s so that nvidia-smi, which needs a
-    # few hundred ms to start, has samples that bracket the timed region instead of one stray reading
-    # (the number of pre-roll searches must be the same on every rank: the exchange is a collective)
-    qpre = make_queries(centres, a.batch, a.dim, 2024, device)
-    barrier()
-    t_pre = time.perf_counter()
-    for _ in range(3):
-        sharded.search_dev(qpre, a.k)
-    torch.cuda.synchronize()
-    t3 = torch.tensor([(time.perf_counter() - t_pre) / 3], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-    for _ in range(int(min(2000, max(1, 0.6 / max(float(t3.item()), 1e-5))))):
-        sharded.search_dev(qpre, a.k)
-    torch.cuda.synchronize()
-    ms_step, scan_ms, launches = timed_steps(a.batch, a.steps, a.warmup)
+    preroll(a.batch)
+    ms_step, scan_ms, launches, q_last, D_last, I_last = timed_steps(a.batch, a.steps, a.warmup)
     clocks = sampler.finish() if sampler else None
-    e2e_ms, D_last, I_last = timed_e2e(a.batch, a.steps, a.warmup)
+    e2e_ms, q_e2e, D_e2e, I_e2e = timed_e2e(a.batch, a.steps, a.warmup)
+
+    parity = None
+    if not a.no_parity:
+        parity = parity_check(src, lo, hi, q_last, D_last, I_last, a.k, world, device)
+        # the last end-to-end step too (host API): its result must satisfy the same contract
+        pe = parity_check(src, lo, hi, q_e2e.to(device), torch.from_numpy(D_e2e).to(device),
+                          torch.from_numpy(I_e2e).to(device), a.k, world, device)
+        parity["e2e_step"] = {k_: pe[k_] for k_ in ("max_abs_err", "violations", "ranks_identical", "ok")}
+        parity["duplicate_tie"] = dup_tie_check()
+        parity["ok"] = bool(parity["ok"] and pe["ok"] and parity["duplicate_tie"]["ok"])
 
     sweep = {}
     for b in [int(t) for t in a.sweep.split(",") if t.strip()]:
-        m, s_ms, _ = timed_steps(b, max(3, a.steps // 3), 2)
+        m, s_ms, _, _, _, _ = timed_steps(b, max(3, a.steps // 3), 3)
         sweep[str(b)] = {"qps": b / (m / 1e3), "ms_per_step": m, "scan_ms": s_ms,
                          "scan_gbs": (hi - lo) * a.dim * 4 / (s_ms * 1e-3) / 1e9}
 
+    sec_list = []
+    if a.secondary == "auto":
+        sec_list = [16, 1024] if (world == 1 and a.batch == 1) else []
+    elif a.secondary != "none":
+        sec_list = [int(t) for t in a.secondary.split(",") if t.strip()]
+    secondary = {}
+    for b in sec_list:
+        steps_b = max(5, min(a.steps, 20 if b <= 128 else 10))
+        smp = ClockSampler(local_rank) if rank == 0 else None
+        if smp:
+            smp.start()
+        preroll(b)
+        m, s_ms, ln, qb_last, Db, Ib = timed_steps(b, steps_b, 3)
+        clk = smp.finish() if smp else None
+        e_ms, _, _, _ = timed_e2e(b, steps_b, 3)
+        entry = {"config": config_of(a, b), "value": b / (m / 1e3), "unit": "queries/s", "steps": steps_b, "warmup": 3,
+                 "ms_per_step": m, "roofline": roofline_of(b, s_ms),
+                 "e2e": {"value": b / (e_ms / 1e3), "unit": "queries/s", "ms_per_step": e_ms,
+                         "h2d_bytes_per_step": b * a.dim * 4, "d2h_bytes_per_step": b * a.k * 12},
+                 "gpu_launches": ln, "clocks": clk}
+        if not a.no_parity:
+            entry["parity_check"] = parity_check(src, lo, hi, qb_last, Db, Ib, a.k, world, device)
+        secondary[f"batch{b}"] = entry
+
     if rank == 0:
-        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_file):
-            peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
-        else:
-            peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
-        local_bytes = (hi - lo) * a.dim * 4
-        traffic = None
-        tf = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tf):
-            t = json.load(open(tf))
-            if t.get("rows") == hi - lo and t.get("dim") == a.dim and t.get("batch") == a.batch:
-                traffic = t.get("dram_bytes_per_launch")
-        if a.batch < 5:   # K1: CUDA-core scan, HBM-bound; one pass of the row store per <= 8 queries
-            passes = (a.batch + 7) // 8
-            achieved = local_bytes * passes / (scan_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "kernel": "scan_topk_kernel", "bytes_per_launch": local_bytes,
-                        "launch_ms": scan_ms / passes, "peak_source": peak_src}
-        elif a.batch <= 128:  # K2, one 128-query block at most: ONE pass over the rows per search -> HBM is the roofline
-            achieved = local_bytes / (scan_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "kernel": "gemm_topk_kernel (all epochs of a search, compactions included)",
-                        "bytes_per_launch": local_bytes, "launch_ms": scan_ms, "peak_source": peak_src,
-                        "note": "tcgen05 TF32 filter epochs + exact fp32 re-scoring of the candidates"}
-        else:             # K2, several 128-query blocks per row tile: tensor pipe; all epochs of a search timed together
-            flop = 2.0 * a.batch * (hi - lo) * a.dim
-            achieved = flop / (scan_ms * 1e-3) / 1e12
-            if os.path.exists(peaks_file):
-                pk = json.load(open(peaks_file))
-                tpeak = float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"])) / 2.0
-                tsrc = "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 issues at half the bf16 rate; no tf32 measurement exists)"
-            else:
-                tpeak, tsrc = 1400.0 / 2.0, "fallback 1.4 PF bf16 sustained / 2 (B200_PROFILING.md)"
-            terms = 3 if os.environ.get("WB_GEMM_FILTER", "1") == "0" else 1
-            roofline = {"bound": "tensor", "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s", "frac": achieved / tpeak,
-                        "traffic": traffic, "kernel": "gemm2_topk_kernel (all epochs of a search)", "flop_per_search": flop,
-                        "search_ms": scan_ms, "issued_tflops": terms * achieved, "issued_frac": terms * achieved / tpeak,
-                        "note": ("3xTF32 in every epoch: each algorithmic flop is issued 3 times" if terms == 3 else
-                                 "one-term TF32 filter epochs (issued ~ algorithmic flops) + exact fp32 re-scoring; the "
-                                 "kernel is bound by its per-chunk row pipeline, not by the tensor pipe (DESIGN.md 6)"),
-                        "peak_source": tsrc}
         line = {
             "metric": METRIC, "value": a.batch / (ms_step / 1e3), "unit": "queries/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "rows_per_gpu": hi - lo, "parallelism": f"row-shard x{world}",
-                       "l2": "database shard (>= 3.8 GB) is far larger than the 126 MB L2; no flush needed",
-                       "generator": "clustered unit vectors, 4096 centres, noise 0.6, seed 2024/2025"},
-            "roofline": roofline,
+            "dtype": "f32", "data": "synthetic", "config": config_of(a),
+            "shard": {"rows_per_gpu": hi - lo, "parallelism": f"row-shard x{world}",
+                      "exchange": "NVLink peer-memory mailbox kernel (no NCCL on the search path)" if world > 1 else "none"},
+            "roofline": roofline_of(a.batch, scan_ms),
             "e2e": {"value": a.batch / (e2e_ms / 1e3), "unit": "queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": a.batch * a.dim * 4, "d2h_bytes_per_step": a.batch * a.k * 12},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks, "parity_check": parity,
         }
         if sweep:
             line["batch_sweep"] = sweep
+        if secondary:
+            line["secondary"] = secondary
         if world == 1 and not a.no_cpu_baseline:
             n_s = min(a.cpu_sample_rows, hi - lo)
             xs = np.empty((n_s, a.dim), np.float32)
@@ -386,7 +645,15 @@ def run_ours(a):
                           f"oracle/cpu_flat.c orc_flat_search_seq ({simd}) = faiss's own threading (parallel over queries only)",
                 "all_cores": {"value": qpsm, "cores": coresm, "median_s": tm, "fn": "orc_flat_search_mt"},
                 "host": cpu_info()}
-            # spot-check the GPU answer of the last e2e step against the restatement on the sample
+            if "batch1024" in secondary:  # faiss's BLAS path (n >= 20) on the host cores, bounded sample
+                n_b = min(200_000, n_s)
+                q1k = make_queries(centres, 1024, a.dim, 2028, device).cpu().numpy()
+                qpsb, tb, th = cpu_blas(xs[:n_b], q1k, a.k, a.rows)
+                secondary["batch1024"]["cpu_baseline"] = {
+                    "value": qpsb, "unit": "queries/s", "cores": th, "kind": "port",
+                    "sample": f"first {n_b} of {a.rows} rows, 1024 queries, 3 reps, median {tb:.3f} s scaled x{a.rows / n_b:g}; "
+                              "oracle/cpu.py blas_flat_search = faiss exhaustive_inner_product_blas restated "
+                              "(OpenBLAS sgemm tiles + partial selection)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

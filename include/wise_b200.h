@@ -137,8 +137,9 @@ int wb_tar_read(const char* path, int64_t d, int64_t cap, int64_t* ids_host, flo
 /* ---- introspection for bench.py / tests --------------------------------------------------- */
 /* TF32 tensor-pipe peak (TFLOP/s) of `device`, measured with the library's own instruction shape: back-to-back
  * tcgen05.mma.cta_group::2.kind::tf32 M=256 N=256 K=8 on every SM pair, no loads (the denominator of the
- * batched-search roofline; replaces nothing in the reference). */
-int wb_tf32_peak(int device, int iters, int reps, double* tflops_out, double* ms_out);
+ * batched-search roofline; replaces nothing in the reference).  burst = best single launch of `iters` x 4 MMAs per
+ * pair; sustained (optional) = the second half of `reps` back-to-back launches, i.e. under the settled power cap. */
+int wb_tf32_peak(int device, int iters, int reps, double* tflops_burst_out, double* tflops_sustained_out);
 /* Device pointer and row stride (floats) of the resident row store. */
 int wb_storage(wb_index* h, void** rows_dev, int64_t* ld);
 /* Number of this library's kernels launched on behalf of `h` since creation. */

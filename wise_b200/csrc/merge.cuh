@@ -38,25 +38,34 @@ __device__ __forceinline__ uint64_t merge_load(const MergeParams& p, int64_t q, 
     }
 }
 
+// Barrier among the NT threads that run a selection: the whole CTA (bar_id < 0) or a named barrier (the consumer
+// warps of scan_topk_kernel, whose producer warp has already left).
+template <int NT>
+__device__ __forceinline__ void sel_sync(int bar_id) {
+    if (bar_id < 0) __syncthreads();
+    else named_bar_sync(bar_id, NT);
+}
+
 // Block-level top-k of M candidates produced by load(i), i in [0, M): leaves the k best keys sorted
 // (descending) in buf[0, k).  buf = [ best k | queue ]: round 0 sorts the first S candidates; after
 // that a candidate is queued only if it beats the current k-th best, so almost everything dies on
 // one compare and the buffer is re-sorted only when the queue could overflow.
-template <class Load>
-__device__ __forceinline__ void block_select_topk(uint64_t* buf, int S, int k, int64_t M, Load load, int* cnt) {
-    const int tid = threadIdx.x;
+// NT threads (tid in [0, NT)) sharing barrier bar_id; S >= k + 2 * NT or S >= M.
+template <int NT = kMergeThreads, class Load>
+__device__ __forceinline__ void block_select_topk(uint64_t* buf, int S, int k, int64_t M, Load load, int* cnt,
+                                                  int tid = threadIdx.x, int bar_id = -1) {
     const int first = (int)min((int64_t)S, M);
-    for (int i = tid; i < S; i += kMergeThreads) buf[i] = i < first ? load((int64_t)i) : 0ull;
+    for (int i = tid; i < S; i += NT) buf[i] = i < first ? load((int64_t)i) : 0ull;
     if (tid == 0) *cnt = 0;
-    __syncthreads();
+    sel_sync<NT>(bar_id);
     // sort only as much as is filled (the rest is zeros = minimal keys): a K2 compaction typically folds a few
     // hundred candidates, and a 4096-key bitonic sort costs ~40 us against ~8 us for 512 keys
-    bitonic_sort_desc<kMergeThreads>(buf, min(S, max(2, pow2_ceil(first))), 1, tid, -1);
+    bitonic_sort_desc<NT>(buf, min(S, max(2, pow2_ceil(first))), 1, tid, bar_id);
     const int qcap = S - k;
-    for (int64_t base = first; base < M; base += kMergeThreads) {
+    for (int64_t base = first; base < M; base += NT) {
         if (base == first)
-            for (int i = k + tid; i < S; i += kMergeThreads) buf[i] = 0ull;
-        __syncthreads();
+            for (int i = k + tid; i < S; i += NT) buf[i] = 0ull;
+        sel_sync<NT>(bar_id);
         const uint64_t thr = buf[k - 1];
         const int64_t c = base + tid;
         const uint64_t key = c < M ? load(c) : 0ull;
@@ -68,18 +77,18 @@ __device__ __forceinline__ void block_select_topk(uint64_t* buf, int S, int k, i
             slot0 = __shfl_sync(0xffffffffu, slot0, 0);
             if (pass) buf[k + slot0 + __popc(m & ((1u << (tid & 31)) - 1))] = key;
         }
-        __syncthreads();
-        if (*cnt > qcap - kMergeThreads) {  // uniform: cnt is read after the barrier
-            bitonic_sort_desc<kMergeThreads>(buf, S, 1, tid, -1);
-            for (int i = k + tid; i < S; i += kMergeThreads) buf[i] = 0ull;
+        sel_sync<NT>(bar_id);
+        if (*cnt > qcap - NT) {  // uniform: cnt is read after the barrier
+            bitonic_sort_desc<NT>(buf, S, 1, tid, bar_id);
+            for (int i = k + tid; i < S; i += NT) buf[i] = 0ull;
             if (tid == 0) *cnt = 0;
-            __syncthreads();
+            sel_sync<NT>(bar_id);
         }
     }
-    __syncthreads();
+    sel_sync<NT>(bar_id);
     // buf = [k sorted best | *cnt queued | zeros]
-    if (*cnt > 0) bitonic_sort_desc<kMergeThreads>(buf, min(S, max(2, pow2_ceil(k + *cnt))), 1, tid, -1);
-    __syncthreads();
+    if (*cnt > 0) bitonic_sort_desc<NT>(buf, min(S, max(2, pow2_ceil(k + *cnt))), 1, tid, bar_id);
+    sel_sync<NT>(bar_id);
 }
 
 // Top-k of `nlists` SORTED (descending) lists of k keys each, load(list, rank) -> key.  Round 0 sorts only
@@ -87,27 +96,27 @@ __device__ __forceinline__ void block_select_topk(uint64_t* buf, int S, int k, i
 // threshold, and because the lists are sorted one compare per list decides whether anything deeper can
 // matter.  Lists that do reach deeper push their surviving tail; if that ever overflows the queue the
 // caller falls back to the generic block_select_topk.  Returns false on overflow (uniform).
-template <class Load2>
-__device__ __forceinline__ bool block_select_topk_lists(uint64_t* buf, int S, int k, int nlists, Load2 load, int* cnt) {
-    const int tid = threadIdx.x;
+template <int NT = kMergeThreads, class Load2>
+__device__ __forceinline__ bool block_select_topk_lists(uint64_t* buf, int S, int k, int nlists, Load2 load, int* cnt,
+                                                        int tid = threadIdx.x, int bar_id = -1) {
     // round 0 depth: ~4x the expected share of a list in the global top-k (+ slack), at most what fits
     const int j_fit = max(1, S / max(nlists, 1));
     const int j0 = min(k, min(j_fit, max(4, (4 * k + nlists - 1) / max(nlists, 1) + 3)));
     const int n0 = nlists * j0;
     if (n0 > S) return false;  // more lists than buffer entries (uniform)
-    for (int i = tid; i < S; i += kMergeThreads) buf[i] = i < n0 ? load(i / j0, i % j0) : 0ull;
+    for (int i = tid; i < S; i += NT) buf[i] = i < n0 ? load(i / j0, i % j0) : 0ull;
     if (tid == 0) *cnt = 0;
-    __syncthreads();
+    sel_sync<NT>(bar_id);
     int Ps = 2;
     while (Ps < n0) Ps <<= 1;  // sort only as much as is filled
     Ps = max(Ps, 2);
-    bitonic_sort_desc<kMergeThreads>(buf, min(Ps, S), 1, tid, -1);
+    bitonic_sort_desc<NT>(buf, min(Ps, S), 1, tid, bar_id);
     if (j0 >= k) return true;
     const int qcap = S - k;
-    for (int i = k + tid; i < S; i += kMergeThreads) buf[i] = 0ull;
-    __syncthreads();
+    for (int i = k + tid; i < S; i += NT) buf[i] = 0ull;
+    sel_sync<NT>(bar_id);
     const uint64_t thr = buf[k - 1];
-    for (int l = tid; l < nlists; l += kMergeThreads) {
+    for (int l = tid; l < nlists; l += NT) {
         for (int r = j0; r < k; ++r) {
             const uint64_t key = load(l, r);
             if (!(key > thr)) break;  // sorted list: nothing below can pass either
@@ -115,15 +124,15 @@ __device__ __forceinline__ bool block_select_topk_lists(uint64_t* buf, int S, in
             if (slot < qcap) buf[k + slot] = key;
         }
     }
-    __syncthreads();
+    sel_sync<NT>(bar_id);
     const int c = *cnt;
     if (c > qcap) return false;
     if (c > 0) {
         int P2 = 2;
         while (P2 < k + c) P2 <<= 1;
-        bitonic_sort_desc<kMergeThreads>(buf, min(P2, S), 1, tid, -1);
+        bitonic_sort_desc<NT>(buf, min(P2, S), 1, tid, bar_id);
     }
-    __syncthreads();
+    sel_sync<NT>(bar_id);
     return true;
 }
 
