@@ -108,9 +108,16 @@ int wb_exch_local_handle(wb_exchange* ex, void* handle64 /* 64 bytes out */);
 int wb_exch_open_peers(wb_exchange* ex, const void* handles /* [world][64] */);
 int wb_exch_merge_dev(wb_exchange* ex, int64_t nq, int64_t k, const float* D_local_dev, const int64_t* I_local_dev,
                       float* D_dev, int64_t* I_dev, void* stream);
-/* index.search(x, k) on a row-sharded index, host buffers in and out (every rank passes the same queries). */
+/* index.search(x, k) on a row-sharded index (every rank passes the same queries): local search + exchange + merge.
+ * Searches served by the scan kernel (flat batches <= 4, every IVF list scan) are ONE launch per GPU: the last CTA of
+ * the scan merges the per-CTA lists, pushes the winners to the peers' mailboxes and emits the global top-k. */
 int wb_exch_search(wb_index* h, wb_exchange* ex, int64_t nq, const float* q_host, int64_t k, int64_t nprobe,
                    float* D_host, int64_t* I_host);
+int wb_exch_search_dev(wb_index* h, wb_exchange* ex, int64_t nq, const float* q_dev, int64_t k, int64_t nprobe,
+                       float* D_dev, int64_t* I_dev, void* stream);
+/* *timed_out = 1 when a kernel of this exchange gave up waiting for a peer (20 s): that search's results are invalid.
+ * wb_exch_search checks it itself; callers of the _dev entry points check it after synchronising their stream. */
+int wb_exch_status(wb_exchange* ex, int* timed_out);
 int wb_exch_free(wb_exchange* ex);
 
 /* ---- row access ------------------------------------------------------------------------- */

@@ -37,6 +37,12 @@ def _worker(rank, world, port, out, mode):
             for rep in range(3):  # repeated calls exercise the double-buffered mailboxes
                 D, I = sh.search(xq, k)
             res[f"D{nq}_{k}"], res[f"I{nq}_{k}"] = D, I
+            # device-buffer entry point (wb_exch_search_dev: one launch when the scan kernel serves the batch)
+            Dd, Id = sh.search_dev(torch.from_numpy(xq).cuda(rank), k)
+            torch.cuda.synchronize()
+            assert np.array_equal(Dd.cpu().numpy(), D) and np.array_equal(Id.cpu().numpy(), I)
+            if sh.exchange is not None:
+                assert not sh.exchange.timed_out()
         np.savez(os.path.join(out, f"{mode}_r{rank}.npz"), **res)
     finally:
         dist.destroy_process_group()

@@ -77,6 +77,27 @@ struct DevBuf {
     T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// Grow-only pinned host buffer (cudaHostAlloc): a copy between pageable memory and the device is staged by the
+// driver and blocks the call; small transfers go through this buffer instead and stay asynchronous.
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) CK(cudaFreeHost(p));
+        p = nullptr;
+        cap = 0;
+        const size_t want = std::max(bytes, (size_t)1 << 16);
+        CK(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
 struct wb_index {
     int device = 0;
     int d = 0, ld = 0;
@@ -98,7 +119,8 @@ struct wb_index {
     bool csr_dirty = true;
     bool contiguous = false;  // rows physically grouped by list (perm is the identity and not stored)
     // scratch
-    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gimg2, gkeys, gstate, gmargin, eD, eI;
+    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gimg2, gkeys, gstate, gmargin, eD, eI, tailcnt;
+    PinBuf pin_q, pin_o;  // pinned staging of small query / result transfers of the host API
     int64_t gemm_launches = 0, gemm_fallbacks = 0;
     // device properties
     int sm_count = 148;
@@ -174,8 +196,10 @@ extern "C" int wb_free(wb_index* h) {
     cudaFree(h->perm);
     cudaFree(h->list_off);
     for (DevBuf* b : {&h->parts, &h->qbuf, &h->dbuf, &h->ibuf, &h->pD, &h->pI, &h->xbuf, &h->idbuf, &h->misc,
-                      &h->kperm, &h->koff, &h->gimg, &h->gimg2, &h->gkeys, &h->gstate, &h->gmargin, &h->eD, &h->eI})
+                      &h->kperm, &h->koff, &h->gimg, &h->gimg2, &h->gkeys, &h->gstate, &h->gmargin, &h->eD, &h->eI, &h->tailcnt})
         b->release();
+    h->pin_q.release();
+    h->pin_o.release();
     for (int i = 0; i < wb_index::kEvRing; ++i) {
         cudaEventDestroy(h->ev0[i]);
         cudaEventDestroy(h->ev1[i]);
@@ -361,9 +385,9 @@ static int launch_scan(const ScanCfg& c, bool gather, ScanParams& p, dim3 grid, 
 }
 
 // Sort-buffer size of the merge: everything at once when it is small, else k + a 2048-entry queue.
-static int merge_buffer_entries(int k, int64_t nparts) {
+static int merge_buffer_entries(int k, int64_t nparts, int nthreads = kMergeThreads) {
     const int64_t M = nparts * (int64_t)k;
-    const int full = pow2_ceil(k + 2 * kMergeThreads);
+    const int full = pow2_ceil(k + 2 * nthreads);
     if (M <= full) return std::max(2, pow2_ceil((int)std::max<int64_t>(M, k)));
     return full;
 }
@@ -398,9 +422,50 @@ static int launch_merge_keys(wb_index* h, int64_t nq, int k, int64_t nparts, con
     return 0;
 }
 
-// Exhaustive top-k of `nq` device queries (row stride ld) against `nrows` rows: K1 + K3.
+// Arrival counters of the fused tail merge: zero between launches (the last CTA of a group resets its own).
+constexpr int64_t kMaxGridY = 32768;
+static int ensure_tail_counters(wb_index* h, cudaStream_t st) {
+    if (h->tailcnt.p) return 0;
+    TRY(h->tailcnt.ensure((size_t)kMaxGridY * sizeof(unsigned int)));
+    CK(cudaMemsetAsync(h->tailcnt.p, 0, (size_t)kMaxGridY * sizeof(unsigned int), st));
+    return 0;
+}
+
+// Can the scan kernel's last CTA run the merge (and the multi-GPU exchange) itself?  The sort buffer and the staged
+// local winners must fit the (then idle) ring.
+static bool tail_fusable(const ScanCfg& c, int k, int64_t nparts, int world, int* S_merge) {
+    if (env_int("WB_FUSE_TAIL", 1) == 0) return false;
+    const int S = std::max(merge_buffer_entries(k, nparts, kConsumerThreads),
+                           world > 1 ? merge_buffer_entries(k, world, kConsumerThreads) : 2);
+    const size_t ring_bytes = (size_t)c.stages * kConsumerWarps * c.RW * c.ck * 4;
+    if ((size_t)S * 8 + (size_t)k * 12 + 64 > ring_bytes) return false;
+    *S_merge = S;
+    return true;
+}
+
+static void set_tail(ScanParams& p, wb_index* h, int S_merge, const int64_t* ids, float* D, int64_t* I, int k,
+                     const ExchParams* ex) {
+    p.fuse_tail = 1;
+    p.S_merge = S_merge;
+    p.tail_count = h->tailcnt.as<unsigned int>();
+    p.ids = ids;
+    p.D = D;
+    p.I = I;
+    p.exchange = 0;
+    if (ex) {
+        p.exchange = 1;
+        p.exch = *ex;
+        p.exch.S = merge_buffer_entries(k, ex->world, kConsumerThreads);
+    }
+}
+
+// Exhaustive top-k of `nq` device queries (row stride ld) against `nrows` rows: K1 with the K3 merge (and, when `ex`
+// is given, the multi-GPU exchange) fused into its tail; K1 + K3 as two launches when the tail cannot be fused.
+// *exchanged tells the caller whether (D, I) already hold the GLOBAL result (written to ex->D / ex->I).
 static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const float* q_dev, int64_t nq, int k,
-                         const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed) {
+                         const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed,
+                         const ExchParams* ex = nullptr, bool* exchanged = nullptr) {
+    if (exchanged) *exchanged = false;
     ScanCfg c;
     TRY(plan_scan(h, nq, k, false, 0, &c));
     const int gr = kConsumerWarps * c.RW;
@@ -418,21 +483,35 @@ static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const fl
     p.ld = h->ld;
     p.k = k;
     p.nparts = (int)S;
+    int S_merge = 0;
+    const bool fuse = tail_fusable(c, k, S, ex ? ex->world : 1, &S_merge);
+    if (fuse) {
+        TRY(ensure_tail_counters(h, st));
+        set_tail(p, h, S_merge, ids, ex ? ex->D : D, ex ? ex->I : I, k, ex);
+    }
     const int evs = (int)(h->ev_count % wb_index::kEvRing);
     if (timed && h->timing) CK(cudaEventRecord(h->ev0[evs], st));
-    const int64_t max_y = 32768;
-    for (int64_t g0 = 0; g0 < qgroups_total; g0 += max_y) {
-        const int64_t gy = std::min(max_y, qgroups_total - g0);
+    for (int64_t g0 = 0; g0 < qgroups_total; g0 += kMaxGridY) {
+        const int64_t gy = std::min(kMaxGridY, qgroups_total - g0);
         const int64_t qoff = g0 * c.NQ;
         p.queries = q_dev + (size_t)qoff * h->ld;
         p.nq = (int)std::min<int64_t>(nq - qoff, gy * c.NQ);
         p.parts = h->parts.as<uint64_t>() + (size_t)qoff * S * k;
+        if (fuse) {  // the tail indexes (D, I) and the mailboxes by the query number inside this launch
+            p.D = (ex ? ex->D : D) + (size_t)qoff * k;
+            p.I = (ex ? ex->I : I) + (size_t)qoff * k;
+            if (ex && qoff != 0) return fail("exchange-fused scans take at most %lld query groups", (long long)kMaxGridY);
+        }
         TRY(launch_scan(c, false, p, dim3((unsigned)S, (unsigned)gy), st));
         h->launches++;
     }
     if (timed && h->timing) {
         CK(cudaEventRecord(h->ev1[evs], st));
         h->ev_count++;
+    }
+    if (fuse) {
+        if (ex && exchanged) *exchanged = true;
+        return 0;
     }
     return launch_merge_keys(h, nq, k, S, h->parts.as<uint64_t>(), ids, D, I, st);
 }
@@ -769,14 +848,13 @@ static int run_assign_gemm(wb_index* h, const float* x_ld, int64_t n, int32_t* a
     return 0;
 }
 
-static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const float* q_dev, int64_t nq, int k,
-                         const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed);
-
 // Exhaustive top-k, any batch size: tensor cores (K2) when the batch is big enough, else the
 // bandwidth-bound CUDA-core scan (K1).  A candidate-list overflow in K2 (adversarially ordered data)
 // is repaired by re-running the batch through K1.
 static int run_flat_any(wb_index* h, const float* rows, int64_t nrows, const float* q_dev, int64_t nq, int k,
-                        const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed) {
+                        const int64_t* ids, float* D, int64_t* I, cudaStream_t st, bool timed,
+                        const ExchParams* ex = nullptr, bool* exchanged = nullptr) {
+    if (exchanged) *exchanged = false;
     int cap = 0;
     if (gemm_eligible(h, nrows, nq, k, &cap)) {
         const int64_t max_q = 65536;  // bounds the candidate buffers
@@ -791,7 +869,8 @@ static int run_flat_any(wb_index* h, const float* rows, int64_t nrows, const flo
         if (!any_overflow) return 0;
         h->gemm_fallbacks++;
     }
-    return run_flat_scan(h, rows, nrows, q_dev, nq, k, ids, D, I, st, timed);
+    return run_flat_scan(h, rows, nrows, q_dev, nq, k, ids, D, I, st, timed,
+                         ex && nq <= kMaxGridY ? ex : nullptr, exchanged);
 }
 
 // ---- CSR inverted lists (host counting sort; insertion order kept inside each list) ---------
@@ -949,8 +1028,9 @@ extern "C" int wb_ivf_add_preassigned(wb_index* h, int64_t n, const float* x_hos
 
 // ---- search --------------------------------------------------------------------------------
 static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld] */, int64_t k, int64_t nprobe, float* D,
-                           int64_t* I, cudaStream_t st) {
-    if (!h->ivf) return run_flat_any(h, h->rows, h->n, q_ld, nq, (int)k, h->ids, D, I, st, true);
+                           int64_t* I, cudaStream_t st, const ExchParams* ex = nullptr, bool* exchanged = nullptr) {
+    if (exchanged) *exchanged = false;
+    if (!h->ivf) return run_flat_any(h, h->rows, h->n, q_ld, nq, (int)k, h->ids, D, I, st, true, ex, exchanged);
     if (!h->trained) return fail("IndexIVFFlat is not trained");
     int np = (int)std::min<int64_t>(std::max<int64_t>(nprobe, 1), std::min<int64_t>(h->nlist, WB_MAX_K));
     // K4: coarse quantizer = exhaustive scan of the centroids, top-nprobe
@@ -975,21 +1055,35 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
     p.perm = h->contiguous ? nullptr : h->perm;
     p.list_off = h->list_off;
     p.nprobe = np;
+    if (ex && nq > kMaxGridY) ex = nullptr;
+    int S_merge = 0;
+    const bool fuse = tail_fusable(c, (int)k, S, ex ? ex->world : 1, &S_merge);
+    if (fuse) {
+        TRY(ensure_tail_counters(h, st));
+        set_tail(p, h, S_merge, h->ids, ex ? ex->D : D, ex ? ex->I : I, (int)k, ex);
+    }
     const int evs = (int)(h->ev_count % wb_index::kEvRing);
     if (h->timing) CK(cudaEventRecord(h->ev0[evs], st));
-    const int64_t max_y = 32768;
-    for (int64_t q0 = 0; q0 < nq; q0 += max_y) {
-        const int64_t gy = std::min(max_y, nq - q0);
+    for (int64_t q0 = 0; q0 < nq; q0 += kMaxGridY) {
+        const int64_t gy = std::min(kMaxGridY, nq - q0);
         p.queries = q_ld + (size_t)q0 * h->ld;
         p.nq = (int)gy;
         p.probes = h->pI.as<int64_t>() + (size_t)q0 * np;
         p.parts = h->parts.as<uint64_t>() + (size_t)q0 * S * k;
+        if (fuse) {
+            p.D = (ex ? ex->D : D) + (size_t)q0 * k;
+            p.I = (ex ? ex->I : I) + (size_t)q0 * k;
+        }
         TRY(launch_scan(c, true, p, dim3((unsigned)S, (unsigned)gy), st));
         h->launches++;
     }
     if (h->timing) {
         CK(cudaEventRecord(h->ev1[evs], st));
         h->ev_count++;
+    }
+    if (fuse) {
+        if (ex && exchanged) *exchanged = true;
+        return 0;
     }
     return launch_merge_keys(h, nq, (int)k, S, h->parts.as<uint64_t>(), h->ids, D, I, st);
 }
@@ -1002,20 +1096,29 @@ static int check_search_args(const wb_index* h, int64_t nq, const void* q, int64
     return 0;
 }
 
+constexpr size_t kPinStageMax = (size_t)4 << 20;  // larger transfers are bandwidth-bound anyway: copy them directly
+
 // queries arrive with row stride d; the kernels want stride ld
 static int stage_queries(wb_index* h, int64_t nq, const float* q, bool host, cudaStream_t st, const float** out) {
     if (!host && h->ld == h->d) {
         *out = q;
         return 0;
     }
+    const size_t qbytes = (size_t)nq * h->d * sizeof(float);
+    if (host && qbytes <= kPinStageMax) {  // pageable -> pinned (host memcpy) -> device (async)
+        PinBuf& pb = h->pin_q;
+        TRY(pb.ensure(qbytes));
+        memcpy(pb.p, q, qbytes);
+        q = reinterpret_cast<const float*>(pb.p);
+    }
     TRY(h->qbuf.ensure((size_t)nq * h->ld * sizeof(float)));
     if (h->ld == h->d) {
-        CK(cudaMemcpyAsync(h->qbuf.p, q, (size_t)nq * h->d * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->qbuf.p, q, qbytes, cudaMemcpyHostToDevice, st));
     } else {
         const float* src = q;
         if (host) {
-            TRY(h->xbuf.ensure((size_t)nq * h->d * sizeof(float)));
-            CK(cudaMemcpyAsync(h->xbuf.p, q, (size_t)nq * h->d * sizeof(float), cudaMemcpyHostToDevice, st));
+            TRY(h->xbuf.ensure(qbytes));
+            CK(cudaMemcpyAsync(h->xbuf.p, q, qbytes, cudaMemcpyHostToDevice, st));
             src = h->xbuf.as<float>();
         }
         const int64_t tot = nq * h->ld;
@@ -1024,6 +1127,27 @@ static int stage_queries(wb_index* h, int64_t nq, const float* q, bool host, cud
         h->launches++;
     }
     *out = h->qbuf.as<float>();
+    return 0;
+}
+
+// (D, I) device -> caller's host buffers, then ONE synchronisation of the stream.
+static int fetch_results(wb_index* h, int64_t nq, int64_t k, const float* D_dev, const int64_t* I_dev, float* D_host,
+                         int64_t* I_host, cudaStream_t st) {
+    const size_t dbytes = (size_t)nq * k * sizeof(float), ibytes = (size_t)nq * k * sizeof(int64_t);
+    if (dbytes + ibytes <= kPinStageMax) {
+        PinBuf& pb = h->pin_o;
+        TRY(pb.ensure(dbytes + ibytes));
+        unsigned char* stage = reinterpret_cast<unsigned char*>(pb.p);
+        CK(cudaMemcpyAsync(stage, I_dev, ibytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(stage + ibytes, D_dev, dbytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(I_host, stage, ibytes);
+        memcpy(D_host, stage + ibytes, dbytes);
+        return 0;
+    }
+    CK(cudaMemcpyAsync(D_host, D_dev, dbytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(I_host, I_dev, ibytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -1049,10 +1173,7 @@ extern "C" int wb_search(wb_index* h, int64_t nq, const float* q_host, int64_t k
     TRY(h->dbuf.ensure((size_t)nq * k * sizeof(float)));
     TRY(h->ibuf.ensure((size_t)nq * k * sizeof(int64_t)));
     TRY(search_dev_impl(h, nq, q, k, nprobe, h->dbuf.as<float>(), h->ibuf.as<int64_t>(), st));
-    CK(cudaMemcpyAsync(D_host, h->dbuf.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(I_host, h->ibuf.p, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return 0;
+    return fetch_results(h, nq, k, h->dbuf.as<float>(), h->ibuf.as<int64_t>(), D_host, I_host, st);
 }
 
 extern "C" int wb_merge_topk_dev(int device, int64_t nq, int64_t k, int64_t nparts, const float* D_parts_dev,
@@ -1354,6 +1475,7 @@ extern "C" int wb_tf32_peak(int device, int iters, int reps, double* tflops_burs
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail("device %d is not sm_100", device);
     const int npairs = prop.multiProcessorCount / 2;
+    const int constant_ops = env_int("WB_PEAK_CONSTANT", 0);  // 1: all-ones operands (no bit toggling: less power, higher clock)
     const size_t smem = (size_t)kF2StageBytes + 1024;
     CK(cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1;
@@ -1363,7 +1485,7 @@ extern "C" int wb_tf32_peak(int device, int iters, int reps, double* tflops_burs
     float best = 1e30f;
     for (int r = 0; r < 4; ++r) {  // burst: best single launch (the first one is the warm-up)
         CK(cudaEventRecord(e0, 0));
-        tf32_peak_kernel<<<2 * npairs, 128, smem, 0>>>(iters);
+        tf32_peak_kernel<<<2 * npairs, 128, smem, 0>>>(iters, constant_ops);
         CK(cudaGetLastError());
         CK(cudaEventRecord(e1, 0));
         CK(cudaEventSynchronize(e1));
@@ -1374,9 +1496,9 @@ extern "C" int wb_tf32_peak(int device, int iters, int reps, double* tflops_burs
     *tflops_burst_out = flop / (best * 1e-3) / 1e12;
     if (tflops_sustained_out) {  // sustained: `reps` launches back to back, the second half timed (power cap settled)
         const int half = std::max(1, reps / 2);
-        for (int r = 0; r < reps - half; ++r) tf32_peak_kernel<<<2 * npairs, 128, smem, 0>>>(iters);
+        for (int r = 0; r < reps - half; ++r) tf32_peak_kernel<<<2 * npairs, 128, smem, 0>>>(iters, constant_ops);
         CK(cudaEventRecord(e0, 0));
-        for (int r = 0; r < half; ++r) tf32_peak_kernel<<<2 * npairs, 128, smem, 0>>>(iters);
+        for (int r = 0; r < half; ++r) tf32_peak_kernel<<<2 * npairs, 128, smem, 0>>>(iters, constant_ops);
         CK(cudaGetLastError());
         CK(cudaEventRecord(e1, 0));
         CK(cudaEventSynchronize(e1));
@@ -1396,7 +1518,8 @@ struct wb_exchange {
     unsigned char* local = nullptr;
     unsigned char* peers[kExchMaxWorld] = {};
     bool opened[kExchMaxWorld] = {};
-    uint32_t seq = 0;
+    uint32_t seq = 0;       // sequence number of the last exchange that was LAUNCHED (all ranks advance in lockstep)
+    int* status = nullptr;  // device word raised by a kernel whose wait for the peers timed out
 };
 
 extern "C" int wb_exch_create(int device, int rank, int world, int64_t max_queries, int64_t max_entries,
@@ -1417,6 +1540,8 @@ extern "C" int wb_exch_create(int device, int rank, int world, int64_t max_queri
     ex->total_bytes = ex->region_bytes * 2 * world;
     CK(cudaMalloc(&ex->local, ex->total_bytes));
     CK(cudaMemset(ex->local, 0, ex->total_bytes));
+    CK(cudaMalloc(&ex->status, sizeof(int)));
+    CK(cudaMemset(ex->status, 0, sizeof(int)));
     CK(cudaDeviceSynchronize());
     ex->peers[rank] = ex->local;
     *out = ex;
@@ -1455,7 +1580,54 @@ extern "C" int wb_exch_free(wb_exchange* ex) {
     for (int r = 0; r < ex->world; ++r)
         if (ex->opened[r]) cudaIpcCloseMemHandle(ex->peers[r]);
     cudaFree(ex->local);
+    cudaFree(ex->status);
     delete ex;
+    return 0;
+}
+
+// Parameters of the NEXT exchange (sequence number ex->seq + 1).  The caller commits the sequence number with
+// exch_commit() only after the kernel that carries these parameters has been launched successfully: a rank whose
+// launch failed must not drift out of lockstep with its peers.
+static int exch_prepare(wb_exchange* ex, int64_t nq, int64_t k, float* D_dev, int64_t* I_dev, ExchParams* out) {
+    if (!ex) return fail("NULL exchange");
+    if (k < 1 || k > WB_MAX_K) return fail("k=%lld out of range [1, %d]", (long long)k, WB_MAX_K);
+    if (nq < 1 || (size_t)nq > ex->nq_cap || (size_t)(nq * k) > ex->cap_entries)
+        return fail("exchange capacity exceeded (nq=%lld, k=%lld)", (long long)nq, (long long)k);
+    for (int r = 0; r < ex->world; ++r)
+        if (!ex->peers[r]) return fail("peer %d is not mapped: call wb_exch_open_peers first", r);
+    ExchParams p{};
+    p.rank = ex->rank;
+    p.world = ex->world;
+    p.nq = nq;
+    p.k = (int)k;
+    p.S = merge_buffer_entries((int)k, ex->world);
+    p.seq = ex->seq + 1;
+    if (p.seq == 0) p.seq = 1;
+    for (int r = 0; r < ex->world; ++r) p.mailbox[r] = ex->peers[r];
+    p.region_bytes = ex->region_bytes;
+    p.flags_bytes = ex->flags_bytes;
+    p.cap_entries = ex->cap_entries;
+    p.D = D_dev;
+    p.I = I_dev;
+    p.status = ex->status;
+    *out = p;
+    return 0;
+}
+static void exch_commit(wb_exchange* ex, const ExchParams& p) { ex->seq = p.seq; }
+
+static int launch_exchange_kernel(wb_exchange* ex, ExchParams& p, const float* D_local, const int64_t* I_local,
+                                  cudaStream_t st) {
+    p.D_local = D_local;
+    p.I_local = I_local;
+    p.S = merge_buffer_entries(p.k, p.world);
+    static thread_local bool attr_done[64] = {};
+    if (ex->device >= 64 || !attr_done[ex->device]) {
+        CK(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        if (ex->device < 64) attr_done[ex->device] = true;
+    }
+    exchange_merge_kernel<<<(unsigned)p.nq, kMergeThreads, (size_t)p.S * 8, st>>>(p);
+    CK(cudaGetLastError());
+    exch_commit(ex, p);
     return 0;
 }
 
@@ -1463,36 +1635,18 @@ extern "C" int wb_exch_free(wb_exchange* ex) {
 // Every rank must call this the same number of times with the same nq and k.
 extern "C" int wb_exch_merge_dev(wb_exchange* ex, int64_t nq, int64_t k, const float* D_local_dev,
                                  const int64_t* I_local_dev, float* D_dev, int64_t* I_dev, void* stream) {
-    if (!ex) return fail("NULL exchange");
-    if (k < 1 || k > WB_MAX_K) return fail("k=%lld out of range [1, %d]", (long long)k, WB_MAX_K);
-    if (nq < 1 || (size_t)nq > ex->nq_cap || (size_t)(nq * k) > ex->cap_entries)
-        return fail("exchange capacity exceeded (nq=%lld, k=%lld)", (long long)nq, (long long)k);
-    for (int r = 0; r < ex->world; ++r)
-        if (!ex->peers[r]) return fail("peer %d is not mapped: call wb_exch_open_peers first", r);
+    ExchParams p;
+    TRY(exch_prepare(ex, nq, k, D_dev, I_dev, &p));
     CK(cudaSetDevice(ex->device));
-    ExchParams p{};
-    p.rank = ex->rank;
-    p.world = ex->world;
-    p.nq = nq;
-    p.k = (int)k;
-    p.S = merge_buffer_entries((int)k, ex->world);
-    p.seq = ++ex->seq;
-    if (p.seq == 0) p.seq = ++ex->seq;
-    p.D_local = D_local_dev;
-    p.I_local = I_local_dev;
-    for (int r = 0; r < ex->world; ++r) p.mailbox[r] = ex->peers[r];
-    p.region_bytes = ex->region_bytes;
-    p.flags_bytes = ex->flags_bytes;
-    p.cap_entries = ex->cap_entries;
-    p.D = D_dev;
-    p.I = I_dev;
-    static thread_local bool attr_done[64] = {};
-    if (ex->device >= 64 || !attr_done[ex->device]) {
-        CK(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-        if (ex->device < 64) attr_done[ex->device] = true;
-    }
-    exchange_merge_kernel<<<(unsigned)nq, kMergeThreads, (size_t)p.S * 8, (cudaStream_t)stream>>>(p);
-    CK(cudaGetLastError());
+    return launch_exchange_kernel(ex, p, D_local_dev, I_local_dev, (cudaStream_t)stream);
+}
+
+// 1 when a kernel of this exchange gave up waiting for a peer (a rank that never launched): the results of that
+// search are invalid.  Reads the device word (synchronises with the kernels that wrote it only if the caller did).
+extern "C" int wb_exch_status(wb_exchange* ex, int* timed_out) {
+    if (!ex || !timed_out) return fail("NULL argument");
+    CK(cudaSetDevice(ex->device));
+    CK(cudaMemcpy(timed_out, ex->status, sizeof(int), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -1561,6 +1715,37 @@ extern "C" int wb_tar_read(const char* path, int64_t d, int64_t cap, int64_t* id
     return 0;
 }
 
+// Search over a row-sharded index, device buffers: local search + NVLink exchange + merge.  Batches that run the
+// scan kernel (flat batch <= 4, every IVF list scan) do all of it in ONE launch (scan.cuh, fused tail); the others
+// run the local search and then exchange_merge_kernel.  Every rank calls it with the same queries.
+static int exch_search_dev_impl(wb_index* h, wb_exchange* ex, int64_t nq, const float* q_ld, int64_t k, int64_t nprobe,
+                                float* D_dev, int64_t* I_dev, cudaStream_t st) {
+    if (ex->device != h->device) return fail("index and exchange live on different devices");
+    ExchParams p;
+    TRY(exch_prepare(ex, nq, k, D_dev, I_dev, &p));
+    TRY(h->dbuf.ensure((size_t)nq * k * sizeof(float)));
+    TRY(h->ibuf.ensure((size_t)nq * k * sizeof(int64_t)));
+    bool exchanged = false;
+    TRY(search_dev_impl(h, nq, q_ld, k, nprobe, h->dbuf.as<float>(), h->ibuf.as<int64_t>(), st, &p, &exchanged));
+    if (exchanged) {
+        exch_commit(ex, p);
+        return 0;
+    }
+    return launch_exchange_kernel(ex, p, h->dbuf.as<float>(), h->ibuf.as<int64_t>(), st);
+}
+
+extern "C" int wb_exch_search_dev(wb_index* h, wb_exchange* ex, int64_t nq, const float* q_dev, int64_t k, int64_t nprobe,
+                                  float* D_dev, int64_t* I_dev, void* stream) {
+    TRY(check_search_args(h, nq, q_dev, k, D_dev, I_dev));
+    if (!ex) return fail("NULL exchange");
+    if (nq == 0) return 0;
+    TRY(set_dev(h));
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* q = nullptr;
+    TRY(stage_queries(h, nq, q_dev, false, st, &q));
+    return exch_search_dev_impl(h, ex, nq, q, k, nprobe, D_dev, I_dev, st);
+}
+
 // Host-buffer search over a sharded index: H2D of the queries, local search, NVLink exchange + merge, D2H of the
 // global (D, I) - one call, one stream, one synchronisation.  Every rank calls it with the same queries.
 extern "C" int wb_exch_search(wb_index* h, wb_exchange* ex, int64_t nq, const float* q_host, int64_t k, int64_t nprobe,
@@ -1568,19 +1753,16 @@ extern "C" int wb_exch_search(wb_index* h, wb_exchange* ex, int64_t nq, const fl
     TRY(check_search_args(h, nq, q_host, k, D_host, I_host));
     if (!ex) return fail("NULL exchange");
     if (nq == 0) return 0;
-    if (ex->device != h->device) return fail("index and exchange live on different devices");
     TRY(set_dev(h));
     cudaStream_t st = h->stream;
     const float* q = nullptr;
     TRY(stage_queries(h, nq, q_host, true, st, &q));
-    TRY(h->dbuf.ensure((size_t)nq * k * sizeof(float)));
-    TRY(h->ibuf.ensure((size_t)nq * k * sizeof(int64_t)));
     TRY(h->eD.ensure((size_t)nq * k * sizeof(float)));
     TRY(h->eI.ensure((size_t)nq * k * sizeof(int64_t)));
-    TRY(search_dev_impl(h, nq, q, k, nprobe, h->dbuf.as<float>(), h->ibuf.as<int64_t>(), st));
-    TRY(wb_exch_merge_dev(ex, nq, k, h->dbuf.as<float>(), h->ibuf.as<int64_t>(), h->eD.as<float>(), h->eI.as<int64_t>(), st));
-    CK(cudaMemcpyAsync(D_host, h->eD.p, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(I_host, h->eI.p, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    TRY(exch_search_dev_impl(h, ex, nq, q, k, nprobe, h->eD.as<float>(), h->eI.as<int64_t>(), st));
+    TRY(fetch_results(h, nq, k, h->eD.as<float>(), h->eI.as<int64_t>(), D_host, I_host, st));
+    int timed_out = 0;
+    CK(cudaMemcpy(&timed_out, ex->status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (timed_out) return fail("sharded search: a peer GPU did not join the exchange within 20 s (results invalid)");
     return 0;
 }

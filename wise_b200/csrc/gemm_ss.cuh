@@ -6,15 +6,15 @@
 // (merge.cuh) re-score the candidates exactly in fp32, so the result is the exact top-k.  Replaces faiss
 // exhaustive_inner_product_blas [faiss-upstream] reached from /root/reference/src/index/feature_search_index.py:113.
 //
-// Why a second kernel (round 2; profiles/r02/gemm_ss.md): at 256+ queries the TS kernel was bound by L2 -> SM
-// traffic, not by its hand-offs: every (row tile, 128-query block) item pulls 16 KB of rows + 8 KB of query image per
-// 32-float chunk for 0.5 M MACs per SM (24 KB x 148 SMs per ~600 cycles = the ~6300 B/cycle the L2 slices deliver).
-// kind::tf32 reads fp32 words and uses their top 19 bits, so the one-term operand needs NO transform at all:
+// Why a second kernel (round 2; profiles/r02/gemm_ss.md): kind::tf32 reads fp32 words and uses their top 19 bits,
+// so the one-term operand needs NO transform at all:
 //   * the raw fp32 row tile lands by 2-D TMA (SWIZZLE_128B) and IS the A operand (K-major SW128 descriptor);
-//   * N = 256 queries per instruction: 16 KB rows + 16 KB image per chunk for 1 M MACs per SM - 1.5x fewer bytes per MAC,
-//     and half as many passes over the rows;
+//   * N = 256 queries per instruction: 16 KB rows + 16 KB image per chunk for 1 M MACs per SM - 1.5x fewer L2 bytes per
+//     MAC than 128-query blocks, and half as many passes over the rows;
 //   * no transform warps, no tcgen05.st, no A slots in tensor memory: TMEM holds two 256-column accumulators, so the
 //     epilogue of one tile still overlaps the MMAs of the next.
+// Measured on B200 (10M x 768, batch 1024): 47.7 -> 27.7 ms per search, bit-identical results; ncu: tensor pipe
+// 97 % active at the power-capped clock (1.27 GHz), L2 -> SM 11.7 TB/s, DRAM 2.2 TB/s.
 // Roles (12 warps): warp 0 producer (TMA rows + bulk copy of this CTA's half image, one barrier per stage),
 // warp 1 MMA issuer (leader) / "my stage landed" forwarder (peer), warp 2 TMEM allocator, warps 4-11 epilogue
 // (TMEM lane quarter = warp & 3, column half = (warp - 4) >> 2).
@@ -272,17 +272,24 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
 
 // ---- TF32 tensor-pipe peak, measured with this library's own instruction shape ------------------------------------
 // Every CTA pair issues `iters` x 4 back-to-back tcgen05.mma.cta_group::2.kind::tf32 (M = 256, N = 256, K = 8, both
-// operands from shared memory - whatever bytes are there; tf32 arithmetic does not care) into two alternating
+// operands from shared memory) into two alternating
 // accumulators and waits for the last commit.  No loads, no epilogue: this is the ceiling filter2_topk_kernel's
 // MMA stream could reach, and the denominator bench.py reports batch-1024 throughput against.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tf32_peak_kernel(int iters, int constant_operands) {
     extern __shared__ __align__(1024) unsigned char smem_pk[];
     unsigned char* st = smem_pk + ((1024u - (smem_u32(smem_pk) & 1023u)) & 1023u);
     __shared__ uint64_t done_bar;
     __shared__ uint32_t tmem_slot_pk;
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool leader = cluster_ctarank() == 0;
-    for (int i = tid; i < kF2StageBytes / 4; i += blockDim.x) reinterpret_cast<float*>(st)[i] = 1.0f;
+    // pseudo-random operands in (-1, 1): the power a tensor pipe draws depends on how many operand bits toggle, and
+    // under the 1 kW cap power sets the clock - constant operands sustained 1116 TFLOP/s at 1.84 GHz on the same GPU
+    // that holds ~1.2-1.3 GHz on real data (profiles/r02/tf32_peak.md)
+    for (int i = tid; i < kF2StageBytes / 4; i += blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+        reinterpret_cast<float*>(st)[i] = constant_operands ? 1.0f : (float)(int32_t)h * (1.0f / 2147483648.0f);
+    }
     if (tid == 0) {
         mbar_init(&done_bar, 1);
         fence_mbar_init();

@@ -203,12 +203,26 @@ __device__ __forceinline__ void rescore_keys(uint64_t* keys, int n, const float*
         const uint32_t pos = key_pos(key);
         const float4* rv = reinterpret_cast<const float4*>(rows + (size_t)pos * ld);
         float acc = 0.f;
-        for (int t = lane; t < ld4; t += 32) {
-            const float4 a = rv[t], b = qv[t];
-            acc = fmaf(a.x, b.x, acc);
-            acc = fmaf(a.y, b.y, acc);
-            acc = fmaf(a.z, b.z, acc);
-            acc = fmaf(a.w, b.w, acc);
+        // all loads of a 256-float4 block are issued before the first FMA (a candidate is one random 2-4 KB row: the
+        // kernel is bound by memory latency x loads in flight); the FMA order is the plain ascending one
+        for (int t0 = 0; t0 < ld4; t0 += 256) {
+            float4 a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + lane + 32 * u;
+                a[u] = t < ld4 ? __ldg(rv + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + lane + 32 * u;
+                if (t < ld4) {
+                    const float4 b = qv[t];
+                    acc = fmaf(a[u].x, b.x, acc);
+                    acc = fmaf(a[u].y, b.y, acc);
+                    acc = fmaf(a[u].z, b.z, acc);
+                    acc = fmaf(a[u].w, b.w, acc);
+                }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

@@ -20,7 +20,7 @@
 //     query at the end, merged by merge_topk_kernel (merge.cuh).
 // Algorithmic bytes per launch: nrows * ld * 4 (the row store is read exactly once per pass).
 #pragma once
-#include "common.cuh"
+#include "exchange.cuh"
 
 namespace wb {
 
@@ -53,6 +53,17 @@ struct ScanParams {
     const int64_t* list_off;  // CSR: [nlist + 1]
     const int64_t* probes;    // [nq][nprobe] list ids (-1 = none)
     int nprobe;
+    // fused tail (K3 inside K1/K5): the LAST CTA of a query group to finish merges the group's nparts lists and
+    // emits (D, I) itself - a search is one launch instead of scan + merge.  With `exchange` set it also pushes the
+    // merged rows to the peer GPUs' mailboxes, waits for theirs and emits the GLOBAL top-k (exchange.cuh).
+    int fuse_tail;
+    int S_merge;              // sort-buffer entries of the fused merge (the idle ring holds them)
+    unsigned int* tail_count; // [gridDim.y] arrival counters, zero between launches (the last CTA resets its own)
+    const int64_t* ids;       // position -> external id (null: id = position)
+    float* D;                 // [nq][k]
+    int64_t* I;
+    int exchange;             // 0: emit local results; 1: exch holds the peer mailboxes
+    ExchParams exch;
 };
 
 struct ScanSmem {
@@ -68,7 +79,7 @@ __host__ __device__ inline ScanSmem scan_smem_layout(int NQ, int ld, int P, int 
     o = (o + 15) & ~(size_t)15;
     L.lists = o;   o += (size_t)NQ * P * 8;
     L.bars = o;    o += (size_t)stages * 2 * 8;
-    L.misc = o;    o += (size_t)NQ * 8;  // qcnt[NQ] (int) + thr_s[NQ] (float)
+    L.misc = o;    o += (size_t)NQ * 8 + 16;  // qcnt[NQ] (int) + thr_s[NQ] (float) + fused-tail flag and counter
     o = (o + 7) & ~(size_t)7;
     L.prefix = o;  o += nprobe > 0 ? (size_t)nprobe * 8 + (size_t)(nprobe + 1) * 4 : 0;  // pbase[np] i64 + prefix[np+1] u32
     L.total = (o + 15) & ~(size_t)15;
@@ -329,6 +340,64 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         for (int i = ctid; i < nqv * k; i += kConsumerThreads) {
             const int l = i / k, j = i - l * k;
             p.parts[((size_t)(q0 + l) * p.nparts + blockIdx.x) * k + j] = lists[(size_t)l * P + j];
+        }
+        if (!p.fuse_tail) return;
+        // ---- fused K3: the last CTA of this query group merges all nparts lists --------------------
+        int& tail_last = reinterpret_cast<int*>(thr_s + NQ)[0];  // (no static shared memory: the layout fills the SM)
+        int& tail_cnt = reinterpret_cast<int*>(thr_s + NQ)[1];
+        __threadfence();  // my keys are visible device-wide before my arrival is
+        named_bar_sync(kBarConsumers, kConsumerThreads);
+        if (ctid == 0) {
+            const unsigned int prev = atomicAdd(&p.tail_count[blockIdx.y], 1u);
+            tail_last = prev == gridDim.x - 1;
+            if (tail_last) p.tail_count[blockIdx.y] = 0;  // ready for the next launch on this stream
+        }
+        named_bar_sync(kBarConsumers, kConsumerThreads);
+        if (!tail_last) return;
+        __threadfence();
+        uint64_t* buf = reinterpret_cast<uint64_t*>(ring);  // the ring is idle: every copy has landed and been consumed
+        for (int l = 0; l < nqv; ++l) {
+            const int64_t q = q0 + l;
+            const uint64_t* src = p.parts + (size_t)q * p.nparts * k;
+            const int64_t M = (int64_t)p.nparts * k;
+            if (!block_select_topk_lists<kConsumerThreads>(
+                    buf, p.S_merge, k, p.nparts, [&](int li, int r) { return __ldcg(src + (size_t)li * k + r); }, &tail_cnt,
+                    ctid, kBarConsumers)) {
+                named_bar_sync(kBarConsumers, kConsumerThreads);
+                block_select_topk<kConsumerThreads>(buf, p.S_merge, k, M, [&](int64_t c) { return __ldcg(src + c); },
+                                                    &tail_cnt, ctid, kBarConsumers);
+            }
+            auto local = [&](int j, float& d, int64_t& id) {
+                const uint64_t key = buf[j];
+                d = -FLT_MAX;
+                id = -1;
+                if (key) {
+                    d = key_score(key);
+                    const uint32_t pos = key_pos(key);
+                    id = p.ids ? p.ids[pos] : (int64_t)pos;
+                }
+            };
+            if (!p.exchange) {
+                for (int j = ctid; j < k; j += kConsumerThreads) {
+                    float d;
+                    int64_t id;
+                    local(j, d, id);
+                    p.D[q * k + j] = d;
+                    p.I[q * k + j] = id;
+                }
+                named_bar_sync(kBarConsumers, kConsumerThreads);  // buf is reused by the next query
+            } else {
+                // the local winners move to the second half of the buffer region: the exchange merge sorts in `buf`
+                float* ld_s = reinterpret_cast<float*>(buf + p.S_merge);
+                int64_t* li_s = reinterpret_cast<int64_t*>(ld_s + ((k + 1) & ~1));
+                for (int j = ctid; j < k; j += kConsumerThreads) local(j, ld_s[j], li_s[j]);
+                named_bar_sync(kBarConsumers, kConsumerThreads);
+                exch_push_wait_merge<kConsumerThreads>(p.exch, q, buf, &tail_cnt, ctid, kBarConsumers,
+                                                       [&](int j, float& d, int64_t& id) {
+                                                           d = ld_s[j];
+                                                           id = li_s[j];
+                                                       });
+            }
         }
     }
 }

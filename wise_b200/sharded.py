@@ -3,9 +3,11 @@ plumbing.
 
 Every rank holds a CONTIGUOUS range of the database rows in its own index (IndexIDMap-style: the
 rows keep their global ids), queries are replicated, each GPU produces its local top-k with the
-same kernels as the single-GPU path, and the only exchange step is one all-gather of the
-`nq * k` (score, id) candidates per rank (NCCL over NVLink; <= 1.2 MB per rank at nq=1024,
-k=100), followed by the K3 merge kernel on every rank.  Because a row's score does not depend on
+same kernels as the single-GPU path, and the only exchange step moves the `nq * k` (score, id)
+candidates of every rank to every other rank (<= 1.2 MB per rank at nq=1024, k=100).  On GPUs that is
+the library's NVLink peer-memory mailbox (csrc/exchange.cuh) - fused into the scan kernel's tail for
+small batches, one extra kernel otherwise; `WISE_B200_EXCHANGE=nccl` (and every CPU/gloo test) takes
+one all-gather followed by the K3 merge kernel instead.  Because a row's score does not depend on
 which GPU holds it and the merge orders ties by (rank, local order) == global insertion position,
 the sharded result is bit-identical to the single-GPU result (tests/test_flat_gpu.py,
 tests/test_sharded_cpu.py).
@@ -84,6 +86,22 @@ class PeerExchange:
                                                             Io.data_ptr(), st))
         return Do, Io
 
+    def search_dev(self, index, q: torch.Tensor, k: int, nprobe: int):
+        """Local search + exchange + merge in one C call (one kernel launch for scan-served searches)."""
+        nq = q.shape[0]
+        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        st = torch.cuda.current_stream(q.device).cuda_stream
+        self._capi.check(self._capi.lib().wb_exch_search_dev(index._h, self.h, nq, q.data_ptr(), k, nprobe, D.data_ptr(),
+                                                             I.data_ptr(), st))
+        return D, I
+
+    def timed_out(self) -> bool:
+        """True when a search gave up waiting for a peer GPU (call after synchronising the stream)."""
+        t = self._C.c_int(0)
+        self._capi.check(self._capi.lib().wb_exch_status(self.h, self._C.byref(t)))
+        return bool(t.value)
+
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
         if h:
@@ -135,12 +153,12 @@ class ShardedIndex:
 
     def search_dev(self, q: torch.Tensor, k: int, nprobe: int = 1):
         """q: [nq, d] float32 tensor, replicated on every rank. Returns merged (D, I) tensors on every rank."""
+        if self.exchange is not None and self.exchange.fits(q.shape[0], k):
+            return self.exchange.search_dev(self.local, q.contiguous(), k, nprobe)
         D, I = self._local_search(self.local, q, k, nprobe)
         if self.world == 1:
             return D, I
         nq, kk = D.shape
-        if self.exchange is not None and self.exchange.fits(nq, kk):
-            return self.exchange.merge(D.contiguous(), I.contiguous())
         Dp = torch.empty((self.world * nq, kk), dtype=D.dtype, device=D.device)
         Ip = torch.empty((self.world * nq, kk), dtype=I.dtype, device=I.device)
         dist.all_gather_into_tensor(Dp, D.contiguous(), group=self.group)  # concatenated along dim 0
