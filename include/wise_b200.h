@@ -17,6 +17,10 @@
  *   - results: D float32[nq*k] sorted by score descending, ties broken by lowest insertion
  *     position; I int64[nq*k]; unfilled slots are (-FLT_MAX, -1) exactly like faiss.
  *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ *   - streams: host-pointer entry points run on the handle's own stream and return synchronised.  "_dev" entry
+ *     points enqueue on the caller's stream; calls on ONE stream are ordered, but the caller must synchronise that
+ *     stream before it uses another stream or a host-pointer entry point on the same handle (an add that has to grow
+ *     the store synchronises the caller's stream itself; wb_reserve up front avoids the growth).
  */
 #ifndef WISE_B200_H
 #define WISE_B200_H
@@ -60,9 +64,22 @@ int wb_reserve(wb_index* h, int64_t n);
 int wb_add_with_ids(wb_index* h, int64_t n, const float* x_host, const int64_t* ids_host);
 int wb_add_with_ids_dev(wb_index* h, int64_t n, const float* x_dev, const int64_t* ids_dev, void* stream);
 
-/* index.train(train_features)   feature_search_index.py:75  (spherical k-means, niter
- * iterations, faiss Clustering defaults: niter=10, seed=1234).  Sets is_trained. */
+/* Pinned, overlapped ingest: the add loop of feature_search_index.py:79-82 with the host->HBM copy and the IVF
+ * assignment of batch i running while the loader decodes batch i+1.  x / ids live in pinned host memory
+ * (wb_pinned_alloc); the call enqueues and returns; `slot` (0..7) names the buffer and wb_add_slot_wait(slot) blocks
+ * until the GPU has finished reading it; wb_sync waits for everything enqueued on the handle. */
+int wb_pinned_alloc(int64_t bytes, void** out);
+int wb_pinned_free(void* p);
+int wb_add_with_ids_pinned(wb_index* h, int64_t n, const float* x_pinned, const int64_t* ids_pinned, int slot);
+int wb_add_slot_wait(wb_index* h, int slot);
+int wb_sync(wb_index* h);
+
+/* index.train(train_features)   feature_search_index.py:75  (k-means with max-inner-product assignment, niter
+ * iterations, faiss Clustering defaults: niter=10, seed=1234, spherical=false).  Sets is_trained. */
 int wb_ivf_train(wb_index* h, int64_t n, const float* x_host, int niter, int64_t seed);
+/* index.cp.spherical (faiss ClusteringParameters): renormalise the centroids after every update.  Default off, like
+ * the IndexIVFFlat the reference constructs (feature_search_index.py:60). */
+int wb_ivf_set_spherical(wb_index* h, int on);
 /* The quantizer's centroids (what faiss keeps in index.quantizer): used to load a trained
  * index (read_index) and to compare search on the reference's own centroids. */
 int wb_ivf_set_centroids(wb_index* h, const float* centroids_host /* [nlist*d] */);
@@ -73,9 +90,13 @@ int wb_ivf_mark_trained(wb_index* h);
  * sharded trainer can all-reduce sums/counts between the two halves.
  *   assign: x -> int32 list per row, objective = sum of max inner products
  *   accumulate: per-list fp32 sums [nlist*d] and int64 counts [nlist] of the local rows
- *   update: centroids <- normalise(sums/counts), empty lists split (eps = 1/1024) */
+ *   update: centroids <- sums/counts (L2-normalised when spherical), empty lists split (eps = 1/1024) */
 int wb_kmeans_assign_dev(wb_index* h, int64_t n, const float* x_dev, int32_t* assign_dev,
                          double* objective_host, void* stream);
+/* Same, with plain-TF32 scores (one tensor-core term): for TRAINING iterations only - two centroids whose scores differ
+ * by less than ~2e-3 |x||c| may swap.  wb_ivf_train uses it; add-time assignment never does. */
+int wb_kmeans_assign_fast_dev(wb_index* h, int64_t n, const float* x_dev, int32_t* assign_dev,
+                              double* objective_host, void* stream);
 int wb_kmeans_accumulate_dev(wb_index* h, int64_t n, const float* x_dev, const int32_t* assign_dev,
                              float* sums_dev, int64_t* counts_dev, void* stream);
 int wb_kmeans_update_dev(wb_index* h, const float* sums_dev, const int64_t* counts_dev, int64_t n_total,
@@ -124,13 +145,21 @@ int wb_exch_free(wb_exchange* ex);
 /* index.reconstruct_batch(ids)   api/routes.py:1078 (after index.make_direct_map, :907).
  * Looks rows up by external id; an unknown id is an error (faiss raises). */
 int wb_reconstruct_batch(wb_index* h, int64_t m, const int64_t* ids_host, float* out_host /* [m*d] */);
-/* Bulk export for faiss.write_index (feature_search_index.py:84): rows [start,start+n) in
- * insertion order, their ids, and (IVF) their list assignment. Any output may be NULL. */
+/* Bulk export for faiss.write_index (feature_search_index.py:84): storage rows [start,start+n), their ids, and (IVF)
+ * their list assignment.  Storage order is insertion order for flat indices and for IVF indices that have not been
+ * searched / finalized yet; afterwards it is list by list.  Any output may be NULL. */
 int wb_export_rows(wb_index* h, int64_t start, int64_t n, float* x_host, int64_t* ids_host, int32_t* assign_host);
 /* Bulk import for faiss.read_index (feature_search_index.py:96) of an IVF index: rows with a
  * known list assignment (no coarse quantisation is run). */
 int wb_ivf_add_preassigned(wb_index* h, int64_t n, const float* x_host, const int64_t* ids_host,
                            const int32_t* assign_host);
+
+/* IVF: bring the inverted lists up to date now (K8: device histogram + scan + stable scatter, then the row store is
+ * regrouped list by list).  faiss does this inside add_with_ids (invlists->add_entry); here it happens lazily at the
+ * first search after an add, or when this is called (faiss.write_index does, feature_search_index.py:84).  After it,
+ * wb_export_rows returns rows in STORAGE order = list by list, insertion order inside a list. */
+int wb_ivf_finalize(wb_index* h);
+int wb_ivf_list_offsets(wb_index* h, int64_t* list_off_host /* [nlist + 1] */, int* grouped_out);
 
 /* ---- FeatureStore fast ingest (host only, no GPU needed) -----------------------------------------------
  * One pass over a WebdatasetStore shard `<media>-%06d.tar` (src/feature/store/webdataset_store.py:33-35):

@@ -167,7 +167,7 @@ def ivf_search(xb: np.ndarray, ids: np.ndarray | None, assign: np.ndarray, centr
 
 
 # --------------------------------------------------------------------------- #
-# k-means (faiss Clustering, spherical) - used by IndexIVFFlat.train
+# k-means (faiss Clustering; spherical=False is what a plain-constructor IndexIVFFlat uses) - IndexIVFFlat.train
 # --------------------------------------------------------------------------- #
 class FaissRandom:
     """[faiss-upstream: utils/random.cpp RandomGenerator] std::mt19937(seed);
@@ -197,12 +197,12 @@ def rand_perm(n: int, seed: int) -> np.ndarray:
     return perm
 
 
-def kmeans_init(x: np.ndarray, k: int, seed: int = 1234) -> np.ndarray:
+def kmeans_init(x: np.ndarray, k: int, seed: int = 1234, spherical: bool = False) -> np.ndarray:
     """[faiss-upstream: Clustering::train] initial centroids = first k rows of
     rand_perm(nx, seed + 1) (redo 0); spherical => L2-renormalised (no-op for unit rows)."""
     perm = rand_perm(x.shape[0], seed + 1)
     c = x[perm[:k]].astype(np.float32).copy()
-    return _renorm(c)
+    return _renorm(c) if spherical else c
 
 
 def _renorm(c: np.ndarray) -> np.ndarray:
@@ -211,10 +211,11 @@ def _renorm(c: np.ndarray) -> np.ndarray:
     return (c / nrm[:, None]).astype(np.float32)
 
 
-def kmeans_iteration(x: np.ndarray, centroids: np.ndarray, rng: FaissRandom | None = None):
+def kmeans_iteration(x: np.ndarray, centroids: np.ndarray, rng: FaissRandom | None = None, spherical: bool = False):
     """One Clustering iteration [faiss-upstream]: assign by max-IP (IndexFlatIP.search k=1),
     compute_centroids (mean of members; empty clusters keep their old centroid),
-    split_clusters (eps=1/1024), post_process_centroids (spherical L2 renorm).
+    split_clusters (eps=1/1024), post_process_centroids (L2 renorm only when cp.spherical; the IndexIVFFlat the
+    reference builds with the plain constructor has spherical=False, index_factory is what turns it on for IP).
     Reached from index.train(), /root/reference/src/index/feature_search_index.py:75.
     Returns (new_centroids, assign, objective=sum of max-IP, nsplit)."""
     k, d = centroids.shape
@@ -251,17 +252,17 @@ def kmeans_iteration(x: np.ndarray, centroids: np.ndarray, rng: FaissRandom | No
             hass[ci] = hass[cj] // 2
             hass[cj] -= hass[ci]
             nsplit += 1
-    return _renorm(newc), assign, obj, nsplit
+    return (_renorm(newc) if spherical else newc.astype(np.float32)), assign, obj, nsplit
 
 
-def kmeans_train(x: np.ndarray, k: int, niter: int = 10, seed: int = 1234):
+def kmeans_train(x: np.ndarray, k: int, niter: int = 10, seed: int = 1234, spherical: bool = False):
     """IndexIVFFlat.train -> Level1Quantizer::train_q1 -> Clustering::train
-    (niter=10, spherical for METRIC_INNER_PRODUCT, nredo=1) [faiss-upstream]."""
-    c = kmeans_init(x, k, seed)
+    (niter=10, nredo=1, cp.spherical False unless the caller sets it) [faiss-upstream]."""
+    c = kmeans_init(x, k, seed, spherical)
     rng = FaissRandom(seed)
     objs = []
     for _ in range(niter):
-        c, _, obj, _ = kmeans_iteration(x, c, rng)
+        c, _, obj, _ = kmeans_iteration(x, c, rng, spherical)
         objs.append(obj)
     return c, objs
 

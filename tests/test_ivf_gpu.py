@@ -99,15 +99,51 @@ def test_kmeans_one_iteration_matches_oracle(faiss):
     assert np.abs(idx.centroids() - c1_ref).max() < 1e-4
 
 
-def test_train_end_to_end_objective(faiss):
+def test_kmeans_fast_assignment_within_tf32_band(faiss):
+    """wb_kmeans_assign_fast_dev (training only): plain-TF32 scores on the 256-centroid SS kernel.  Every point must land
+    on a centroid whose exact score is within 2e-3 |x||c| of the best one, and almost all on the best one itself."""
+    import ctypes as C
+    import torch
+    from wise_b200 import _capi
+    L = _capi.lib()
+    n, d, k = 50000, 200, 700  # 3 centroid blocks (the last one partial), 7 k-chunks (the last one partial)
+    x = O.clustered_unit(n, d, 900, 12)
+    c0 = O.kmeans_init(x, k)
+    idx = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, k, faiss.METRIC_INNER_PRODUCT)
+    idx.set_centroids(c0)
+    xd = torch.from_numpy(x).cuda()
+    assign = torch.empty(n, dtype=torch.int32, device="cuda")
+    obj = C.c_double(0)
+    st = torch.cuda.current_stream().cuda_stream
+    _capi.check(L.wb_kmeans_assign_fast_dev(idx._h, n, xd.data_ptr(), assign.data_ptr(), C.byref(obj), st))
+    torch.cuda.synchronize()
+    a = assign.cpu().numpy().astype(np.int64)
+    s = x.astype(np.float64) @ c0.astype(np.float64).T
+    best = s.max(axis=1)
+    got = s[np.arange(n), a]
+    assert a.min() >= 0 and a.max() < k
+    assert np.all(best - got <= 2e-3), float((best - got).max())
+    assert (a == s.argmax(axis=1)).mean() > 0.995
+    assert abs(obj.value - best.sum()) < 2e-3 * n
+
+
+@pytest.mark.parametrize("spherical", [False, True])
+def test_train_end_to_end_objective(faiss, spherical):
+    """index.train (plain-TF32 assignment on the SS tensor-core kernel, device-side grouping): same clustering quality
+    as the fp64 oracle run of the same algorithm; cp.spherical as in faiss (default False)."""
     n, d, k = 8000, 64, 50
     x = O.clustered_unit(n, d, 50, 21)
     idx = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, k, faiss.METRIC_INNER_PRODUCT)
+    assert idx.cp.spherical is False and idx.cp.niter == 10
+    idx.cp.spherical = spherical
     idx.train(x)
     assert idx.is_trained and idx.quantizer.ntotal == k
     c = idx.centroids()
-    assert np.allclose(np.linalg.norm(c, axis=1), 1.0, atol=1e-4)
-    c_ref, objs = O.kmeans_train(x, k)
+    if spherical:
+        assert np.allclose(np.linalg.norm(c, axis=1), 1.0, atol=1e-4)
+    else:
+        assert np.all(np.linalg.norm(c, axis=1) <= 1.0 + 1e-4)
+    c_ref, objs = O.kmeans_train(x, k, spherical=spherical)
     obj_gpu = float(np.max(x.astype(np.float64) @ c.astype(np.float64).T, axis=1).sum())
     obj_ref = float(np.max(x.astype(np.float64) @ c_ref.astype(np.float64).T, axis=1).sum())
     assert obj_gpu >= 0.995 * obj_ref, (obj_gpu, obj_ref)
@@ -115,3 +151,71 @@ def test_train_end_to_end_objective(faiss):
     idx.nprobe = 5
     D, I = idx.search(x[:4], 3)
     assert np.array_equal(I[:, 0], np.arange(4))
+
+
+def test_ivf_ties_across_lists_and_regrouping(faiss):
+    """Equal scores in DIFFERENT lists order by insertion position (the Flat rule; the oracle's rule), not by list
+    number: the row store is regrouped list by list on the device (K8) but keys carry the original position.
+    Also: storage-order export after the grouping, adds after a grouping, reconstruct on a grouped store."""
+    from wise_b200 import _capi
+    L = _capi.lib()
+    n, d, nlist = 3000, 32, 8
+    cent = O.unit_gaussian(nlist, d, 3)
+    xb = O.unit_gaussian(n, d, 4)
+    xb[1500] = xb[10]  # exact duplicate at a later insertion position
+    assign = O.ivf_assign(xb, cent).astype(np.int32)
+    assign[10], assign[1500] = 6, 2  # ... and the EARLIER row lives in the LATER list
+    ids = np.arange(n, dtype=np.int64)
+    idx = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, nlist, faiss.METRIC_INNER_PRODUCT)
+    idx.set_centroids(cent)
+    _capi.check(L.wb_ivf_add_preassigned(idx._h, n, _capi.ptr(xb), _capi.ptr(ids), _capi.ptr(assign)))
+    idx.nprobe = nlist
+    xq = np.concatenate([xb[10:11], O.unit_gaussian(5, d, 5)])
+    D, I = idx.search(xq, 20)
+    assert I[0, 0] == 10 and I[0, 1] == 1500 and D[0, 0] == D[0, 1]
+    Dr, Ir = O.ivf_search(xb, ids, assign.astype(np.int64), cent, xq, 20, nlist)
+    O.compare_topk(D, I, Dr, Ir)
+    # storage order after the grouping: list by list, insertion order inside a list, ids follow their rows
+    x, i, a = idx._export(0, n, want_assign=True)
+    assert np.all(np.diff(a) >= 0) and np.array_equal(x, xb[i]) and np.array_equal(a, assign[i])
+    for l in range(nlist):
+        assert np.all(np.diff(i[a == l]) > 0)
+    # adds after a grouping: the next search regroups, old and new rows keep their insertion order
+    x2 = O.unit_gaussian(500, d, 6)
+    x2[7] = xb[10]
+    a2 = O.ivf_assign(x2, cent).astype(np.int32)
+    a2[7] = 0
+    ids2 = np.arange(n, n + 500, dtype=np.int64)
+    _capi.check(L.wb_ivf_add_preassigned(idx._h, 500, _capi.ptr(x2), _capi.ptr(ids2), _capi.ptr(a2)))
+    D, I = idx.search(xq, 20)
+    assert list(I[0, :3]) == [10, 1500, n + 7] and D[0, 0] == D[0, 2]
+    xa, ia, aa = np.concatenate([xb, x2]), np.concatenate([ids, ids2]), np.concatenate([assign, a2]).astype(np.int64)
+    Dr, Ir = O.ivf_search(xa, ia, aa, cent, xq, 20, nlist)
+    O.compare_topk(D, I, Dr, Ir)
+    idx.nprobe = 2
+    D, I = idx.search(xq, 20)
+    Dr, Ir = O.ivf_search(xa, ia, aa, cent, xq, 20, 2)
+    O.compare_topk(D, I, Dr, Ir)
+    # ids are 0..ntotal-1: the direct map exists and reconstruct finds rows in the grouped store
+    idx.make_direct_map(True)
+    assert np.array_equal(idx.reconstruct_batch([10, 1500, n + 7, 2999, 0]), xa[[10, 1500, n + 7, 2999, 0]])
+
+
+def test_ivf_write_index_without_search_is_grouped(faiss, tmp_path):
+    """create_index's order (train, add, write_index - no search): the writer finalizes the lists first, the file
+    round-trips and searches like the original (/root/reference/src/index/feature_search_index.py:75-84)."""
+    n, d, nlist = 20000, 48, 25
+    xb = O.clustered_unit(n, d, 50, 8)
+    ids = np.arange(n, dtype=np.int64) * 3 + 1
+    cent = O.kmeans_init(xb, nlist)
+    idx = _ivf(faiss, xb, ids, cent)
+    fn = str(tmp_path / "image-IndexIVFFlat.faiss")
+    faiss.write_index(idx, fn)
+    idx2 = faiss.read_index(fn, faiss.IO_FLAG_READ_ONLY)
+    assert idx2.ntotal == n and idx2.nlist == nlist
+    xq = O.clustered_unit(4, d, 50, 9)
+    for index in (idx, idx2):
+        index.nprobe = 6
+    D1, I1 = idx.search(xq, 10)
+    D2, I2 = idx2.search(xq, 10)
+    assert np.array_equal(I1, I2) and np.array_equal(D1, D2)

@@ -83,16 +83,23 @@ def test_faiss_random_is_mt19937():
 
 def test_kmeans_objective_improves_and_centroids_unit():
     x = O.clustered_unit(3000, 24, 20, 9)
-    c, objs = O.kmeans_train(x, 20, niter=6)
+    c, objs = O.kmeans_train(x, 20, niter=6, spherical=True)
     assert np.allclose(np.linalg.norm(c, axis=1), 1.0, atol=1e-5)
     assert objs[-1] >= objs[0] and all(b >= a - 1e-3 for a, b in zip(objs, objs[1:]))
+    # faiss's default for the IndexIVFFlat the reference builds (cp.spherical = False): centroids are plain means
+    c2, _ = O.kmeans_train(x, 20, niter=6)
+    assert np.all(np.linalg.norm(c2, axis=1) <= 1.0 + 1e-5) and np.any(np.linalg.norm(c2, axis=1) < 0.999)
+    a2 = O.ivf_assign(x, c2)
+    for l in range(20):
+        if np.any(a2 == l):
+            assert np.abs(O.kmeans_iteration(x, c2)[0][l] - x[a2 == l].astype(np.float64).mean(axis=0)).max() < 1e-5
 
 
 def test_kmeans_split_fills_empty_cluster():
     x = O.clustered_unit(400, 16, 3, 10)
     c = O.kmeans_init(x, 8)
     c[7] = -c[0]  # a centroid nobody is closest to
-    newc, assign, _, nsplit = O.kmeans_iteration(x, c)
+    newc, assign, _, nsplit = O.kmeans_iteration(x, c, spherical=True)
     if not np.any(assign == 7):
         assert nsplit >= 1
     assert np.allclose(np.linalg.norm(newc, axis=1), 1.0, atol=1e-5)

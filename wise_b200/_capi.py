@@ -34,11 +34,18 @@ SIGNATURES = {
     "wb_reserve": (C.c_int, [_vp, C.c_int64]),
     "wb_add_with_ids": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
     "wb_add_with_ids_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),
+    "wb_pinned_alloc": (C.c_int, [C.c_int64, C.POINTER(_vp)]),
+    "wb_pinned_free": (C.c_int, [_vp]),
+    "wb_add_with_ids_pinned": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int]),
+    "wb_add_slot_wait": (C.c_int, [_vp, C.c_int]),
+    "wb_sync": (C.c_int, [_vp]),
     "wb_ivf_train": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, C.c_int64]),
     "wb_ivf_set_centroids": (C.c_int, [_vp, _vp]),
     "wb_ivf_get_centroids": (C.c_int, [_vp, _vp]),
     "wb_ivf_mark_trained": (C.c_int, [_vp]),
+    "wb_ivf_set_spherical": (C.c_int, [_vp, C.c_int]),
     "wb_kmeans_assign_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.POINTER(C.c_double), _vp]),
+    "wb_kmeans_assign_fast_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.POINTER(C.c_double), _vp]),
     "wb_kmeans_accumulate_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "wb_kmeans_update_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.POINTER(C.c_int64), _vp]),
     "wb_search": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, _vp]),
@@ -55,6 +62,8 @@ SIGNATURES = {
     "wb_reconstruct_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
     "wb_export_rows": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp]),
     "wb_ivf_add_preassigned": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),
+    "wb_ivf_finalize": (C.c_int, [_vp]),
+    "wb_ivf_list_offsets": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
     "wb_tar_scan": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "wb_tar_read": (C.c_int, [C.c_char_p, C.c_int64, C.c_int64, _vp, _vp, C.POINTER(C.c_int64)]),
     "wb_tf32_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/wise_b200.h"
+#include "csr.cuh"
 #include "exchange.cuh"
 #include "gemm.cuh"
 #include "gemm_ss.cuh"
@@ -104,6 +105,7 @@ struct wb_index {
     bool ivf = false;
     int64_t nlist = 0;
     bool trained = true;
+    bool spherical = false;  // k-means: L2-renormalise the centroids after every update (faiss cp.spherical)
     cudaStream_t stream = nullptr;
     // row store (insertion order)
     float* rows = nullptr;
@@ -111,16 +113,22 @@ struct wb_index {
     int32_t* assign = nullptr;  // IVF: list of each row
     int64_t n = 0, cap = 0;
     float* norm2_max = nullptr;  // device scalar: max |row|^2 over everything ever added (K2 filter margin)
-    // IVF quantizer + CSR inverted lists (row indices grouped by list, insertion order kept)
-    float* centroids = nullptr;  // [nlist, ld]
-    uint32_t* perm = nullptr;
-    int64_t perm_cap = 0;
+    // IVF quantizer + inverted lists.  `ids` always stay in INSERTION order.  After a (re)grouping the rows are
+    // stored list by list (insertion order kept inside a list): row_pos[row] is then the insertion position of a
+    // storage row - the tie rule and the id lookup - and slot_row is null.  When the transient second copy of the rows
+    // does not fit, the rows stay where they are and slot_row[CSR slot] is the storage row of each list slot.
+    float* centroids = nullptr;   // [nlist, ld]
+    uint32_t* slot_row = nullptr; // [n] or null (slot == storage row)
+    uint32_t* row_pos = nullptr;  // [map_cap] or null (storage row == insertion position)
+    int64_t map_cap = 0;
     int64_t* list_off = nullptr;  // [nlist + 1]
     bool csr_dirty = true;
-    bool contiguous = false;  // rows physically grouped by list (perm is the identity and not stored)
     // scratch
-    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gimg2, gkeys, gstate, gmargin, eD, eI, tailcnt;
+    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gimg2, gkeys, gstate, gmargin, eD, eI, tailcnt, ccnt, ctot;
     PinBuf pin_q, pin_o;  // pinned staging of small query / result transfers of the host API
+    static constexpr int kAddSlots = 8;   // wb_add_with_ids_pinned: one event per in-flight pinned buffer
+    cudaEvent_t add_ev[kAddSlots] = {};
+    bool add_pending[kAddSlots] = {};
     int64_t gemm_launches = 0, gemm_fallbacks = 0;
     // device properties
     int sm_count = 148;
@@ -174,6 +182,7 @@ static int create_common(int d, int device, bool ivf, int64_t nlist, wb_index** 
         CK(cudaMalloc(&h->list_off, (size_t)(nlist + 1) * sizeof(int64_t)));
         CK(cudaMemsetAsync(h->list_off, 0, (size_t)(nlist + 1) * sizeof(int64_t), h->stream));
     }
+    CK(cudaStreamSynchronize(h->stream));  // the zero-fills above must not race a first add on another stream
     *out = h;
     return 0;
 }
@@ -193,13 +202,16 @@ extern "C" int wb_free(wb_index* h) {
     cudaFree(h->assign);
     cudaFree(h->centroids);
     cudaFree(h->norm2_max);
-    cudaFree(h->perm);
+    cudaFree(h->slot_row);
+    cudaFree(h->row_pos);
     cudaFree(h->list_off);
     for (DevBuf* b : {&h->parts, &h->qbuf, &h->dbuf, &h->ibuf, &h->pD, &h->pI, &h->xbuf, &h->idbuf, &h->misc,
-                      &h->kperm, &h->koff, &h->gimg, &h->gimg2, &h->gkeys, &h->gstate, &h->gmargin, &h->eD, &h->eI, &h->tailcnt})
+                      &h->kperm, &h->koff, &h->gimg, &h->gimg2, &h->gkeys, &h->gstate, &h->gmargin, &h->eD, &h->eI, &h->tailcnt, &h->ccnt, &h->ctot})
         b->release();
     h->pin_q.release();
     h->pin_o.release();
+    for (int i = 0; i < wb_index::kAddSlots; ++i)
+        if (h->add_ev[i]) cudaEventDestroy(h->add_ev[i]);
     for (int i = 0; i < wb_index::kEvRing; ++i) {
         cudaEventDestroy(h->ev0[i]);
         cudaEventDestroy(h->ev1[i]);
@@ -264,6 +276,15 @@ static int ensure_capacity(wb_index* h, int64_t need) {
     CK(cudaMalloc(&nrows, (size_t)newcap * h->ld * sizeof(float)));
     CK(cudaMalloc(&nids, (size_t)newcap * sizeof(int64_t)));
     if (h->ivf) CK(cudaMalloc(&nas, (size_t)newcap * sizeof(int32_t)));
+    if (h->row_pos && newcap > h->map_cap) {
+        uint32_t* np_ = nullptr;
+        CK(cudaMalloc(&np_, (size_t)newcap * sizeof(uint32_t)));
+        if (h->n > 0) CK(cudaMemcpyAsync(np_, h->row_pos, (size_t)h->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->row_pos);
+        h->row_pos = np_;
+        h->map_cap = newcap;
+    }
     if (h->n > 0) {
         CK(cudaMemcpyAsync(nrows, h->rows, (size_t)h->n * h->ld * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
         CK(cudaMemcpyAsync(nids, h->ids, (size_t)h->n * sizeof(int64_t), cudaMemcpyDeviceToDevice, h->stream));
@@ -701,7 +722,7 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
             if (use_f2 && one_term) {  // 256-query blocks, both operands from shared memory
                 static thread_local bool a3[64] = {};
                 if (dev >= 64 || !a3[dev]) {
-                    CK(cudaFuncSetAttribute(filter2_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                    CK(cudaFuncSetAttribute(filter2_topk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)kF2SmemBytes));
                     if (dev < 64) a3[dev] = true;
                 }
@@ -710,7 +731,7 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
                 g2.bimg = h->gimg2.as<float>();
                 const int64_t ntp = ((r1 - r0 + kGemmBM - 1) / kGemmBM + 1) / 2;
                 const unsigned grid3 = 2u * (unsigned)std::min<int64_t>(ntp * nqb2, h->sm_count / 2);
-                filter2_topk_kernel<false><<<grid3, kF2Threads, kF2SmemBytes, st>>>(tmap, g2);
+                filter2_topk_kernel<false, false><<<grid3, kF2Threads, kF2SmemBytes, st>>>(tmap, g2);
                 launched = true;
             }
         }
@@ -783,11 +804,54 @@ static bool assign_gemm_eligible(const wb_index* h, int64_t n) {
 }
 
 static int run_assign_gemm(wb_index* h, const float* x_ld, int64_t n, int32_t* assign_out, float* best_out,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool tf32 = false) {
     constexpr int BN = 128;
     using Cfg = GemmCfg<BN>;
     const int ld = h->ld;
     const int nchunks = (ld + kGemmBK - 1) / kGemmBK;
+    if (tf32 && (h->sm_count % 2) == 0 && env_int("WB_GEMM_2CTA", 1) != 0) {
+        // k-means TRAINING assignment: plain TF32 on the SS pair kernel, 256 centroids per block (gemm_ss.cuh)
+        const int nqb2 = (int)((h->nlist + kF2BN - 1) / kF2BN);
+        TRY(h->gimg2.ensure((size_t)nqb2 * 2 * nchunks * kF2BBytes));
+        const int64_t n4 = (int64_t)nqb2 * 2 * nchunks * 8 * kF2Half;
+        image_queries_f2_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(h->centroids, (int)h->nlist, ld, nchunks, nqb2,
+                                                                             h->gimg2.as<float>());
+        CK(cudaGetLastError());
+        PFN_encodeTiled enc = nullptr;
+        TRY(get_tensormap_encoder(&enc));
+        CUtensorMap tm;
+        cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)n};
+        cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+        cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)kGemmBM};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)x_ld, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        static thread_local bool a4[64] = {};
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        if (dev >= 64 || !a4[dev]) {
+            CK(cudaFuncSetAttribute(filter2_topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kF2SmemBytes));
+            if (dev < 64) a4[dev] = true;
+        }
+        GemmParams g{};
+        g.row_begin = 0;
+        g.row_end = n;
+        g.nchunks = nchunks;
+        g.nq = (int)h->nlist;
+        g.nqb = nqb2;
+        g.bimg = h->gimg2.as<float>();
+        g.assign_out = assign_out;
+        g.best_out = best_out;
+        const int64_t ntp = ((n + kGemmBM - 1) / kGemmBM + 1) / 2;
+        filter2_topk_kernel<true, false><<<2u * (unsigned)std::min<int64_t>(ntp, h->sm_count / 2), kF2Threads, kF2SmemBytes, st>>>(tm, g);
+        CK(cudaGetLastError());
+        h->launches += 2;
+        h->gemm_launches++;
+        return 0;
+    }
     const int nqb = (int)((h->nlist + BN - 1) / BN);
     TRY(h->gimg.ensure((size_t)nqb * nchunks * Cfg::kBBytes));
     const int64_t n2 = (int64_t)nqb * nchunks * 8 * BN;
@@ -873,74 +937,119 @@ static int run_flat_any(wb_index* h, const float* rows, int64_t nrows, const flo
                          ex && nq <= kMaxGridY ? ex : nullptr, exchanged);
 }
 
-// ---- CSR inverted lists (host counting sort; insertion order kept inside each list) ---------
-static int build_csr_host(const int32_t* assign_dev, int64_t n, int64_t nlist, std::vector<uint32_t>& perm,
-                          std::vector<int64_t>& off, cudaStream_t st) {
-    std::vector<int32_t> a((size_t)n);
-    if (n) CK(cudaMemcpyAsync(a.data(), assign_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    off.assign((size_t)nlist + 1, 0);
-    for (int64_t i = 0; i < n; ++i) {
-        if (a[i] < 0 || a[i] >= nlist) return fail("row %lld has invalid list %d", (long long)i, a[i]);
-        off[(size_t)a[i] + 1]++;
+// ---- K8: CSR inverted lists, built on the device (csr.cuh) -------------------------------------------------------
+// Stable grouping of n items by list: list_off[nlist + 1], src[slot] = item index, pos_out[slot] = pos_in[item].
+// Everything is enqueued on `st`; the only host involvement is reading one error word when `check` is set.
+static int device_csr(wb_index* h, const int32_t* assign, int64_t n, const uint32_t* pos_in, int64_t* list_off,
+                      uint32_t* src, uint32_t* pos_out, cudaStream_t st, bool check) {
+    const int64_t nlist = h->nlist;
+    if (n >= (int64_t)0xFFFFFFFFll) return fail("too many items to group");
+    // B blocks of items: enough to fill the GPU, few enough for the [B][nlist] counter matrix to stay small
+    int64_t B = std::min<int64_t>(1024, std::max<int64_t>(1, (n + 4095) / 4096));
+    B = std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)64 << 20) / std::max<int64_t>(nlist, 1)));
+    int64_t ipb = (n + B - 1) / B;
+    ipb = std::max<int64_t>(kCsrTile, (ipb + kCsrTile - 1) / kCsrTile * kCsrTile);
+    B = std::max<int64_t>(1, (n + ipb - 1) / ipb);
+    TRY(h->ccnt.ensure((size_t)B * nlist * sizeof(uint32_t) + 64));
+    TRY(h->ctot.ensure((size_t)nlist * sizeof(int64_t) + 64));
+    uint32_t* cnt = h->ccnt.as<uint32_t>();
+    int* bad = reinterpret_cast<int*>(h->ctot.as<unsigned char>() + (size_t)nlist * sizeof(int64_t));
+    CK(cudaMemsetAsync(cnt, 0, (size_t)B * nlist * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    if (n > 0) {
+        csr_hist_kernel<<<(unsigned)B, kCsrTile, 0, st>>>(assign, n, nlist, ipb, cnt, bad);
+        CK(cudaGetLastError());
     }
-    for (int64_t l = 0; l < nlist; ++l) off[l + 1] += off[l];
-    std::vector<int64_t> cur(off.begin(), off.end() - 1);
-    perm.resize((size_t)n);
-    for (int64_t i = 0; i < n; ++i) perm[(size_t)cur[a[i]]++] = (uint32_t)i;
+    csr_colscan_kernel<<<(unsigned)((nlist + 255) / 256), 256, 0, st>>>(cnt, (int)B, nlist, h->ctot.as<int64_t>());
+    CK(cudaGetLastError());
+    csr_offsets_kernel<<<1, 1024, 0, st>>>(h->ctot.as<int64_t>(), nlist, list_off);
+    CK(cudaGetLastError());
+    if (n > 0) {
+        csr_scatter_kernel<<<(unsigned)B, kCsrTile, 0, st>>>(assign, n, nlist, ipb, cnt, list_off, pos_in, src, pos_out);
+        CK(cudaGetLastError());
+    }
+    h->launches += 4;
+    if (check) {
+        int hb = 0;
+        CK(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (hb) return fail("a row has a list assignment outside [0, %lld)", (long long)nlist);
+    }
     return 0;
 }
 
 // Build the inverted lists.  Default: PHYSICALLY group the row store by list (rows of a list become one
 // contiguous span, insertion order kept inside a list), so the list scan is a sequential HBM stream instead of
 // a gather of 2-3 KB rows (measured 3.3-4.3 TB/s gathered).  Needs a second copy of the rows while it runs; if
-// that does not fit, the lists stay a CSR of row indices over the insertion-ordered store.
+// that does not fit, the lists stay a CSR of row indices (slot_row) over the store as it is.
 static int ensure_csr(wb_index* h) {
     if (!h->csr_dirty) return 0;
-    std::vector<uint32_t> perm;
-    std::vector<int64_t> off;
-    TRY(build_csr_host(h->assign, h->n, h->nlist, perm, off, h->stream));
-    if (h->n > h->perm_cap) {
-        cudaFree(h->perm);
-        h->perm = nullptr;
-        CK(cudaMalloc(&h->perm, (size_t)std::max<int64_t>(h->cap, h->n) * sizeof(uint32_t)));
-        h->perm_cap = std::max<int64_t>(h->cap, h->n);
+    cudaStream_t st = h->stream;
+    const int64_t n = h->n;
+    cudaFree(h->slot_row);
+    h->slot_row = nullptr;
+    if (n == 0) {
+        CK(cudaMemsetAsync(h->list_off, 0, (size_t)(h->nlist + 1) * sizeof(int64_t), st));
+        CK(cudaStreamSynchronize(st));
+        h->csr_dirty = false;
+        return 0;
     }
-    if (h->n) CK(cudaMemcpyAsync(h->perm, perm.data(), (size_t)h->n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->list_off, off.data(), (size_t)(h->nlist + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
-                       h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->contiguous = false;
-    if (h->n > 0 && env_int("WB_IVF_CONTIGUOUS", 1)) {
-        const int64_t ncap = std::max<int64_t>(h->n, 1024);
-        const size_t need = (size_t)ncap * h->ld * 4 + (size_t)ncap * 12;
+    uint32_t* src = nullptr;
+    uint32_t* pos_out = nullptr;
+    const int64_t mcap = std::max<int64_t>(h->cap, n);
+    CK(cudaMalloc(&src, (size_t)n * sizeof(uint32_t)));
+    CK(cudaMalloc(&pos_out, (size_t)mcap * sizeof(uint32_t)));
+    int rc = device_csr(h, h->assign, n, h->row_pos, h->list_off, src, pos_out, st, true);
+    if (rc) {
+        cudaFree(src);
+        cudaFree(pos_out);
+        return rc;
+    }
+    bool grouped = false;
+    if (env_int("WB_IVF_CONTIGUOUS", 1)) {
+        const int64_t ncap = std::max<int64_t>(h->cap, std::max<int64_t>(n, 1024));
+        const size_t need = (size_t)ncap * h->ld * 4 + (size_t)ncap * 4;
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         if (free_b > need + ((size_t)1 << 30)) {
             float* nrows = nullptr;
-            int64_t* nids = nullptr;
             int32_t* nas = nullptr;
             CK(cudaMalloc(&nrows, (size_t)ncap * h->ld * 4));
-            CK(cudaMalloc(&nids, (size_t)ncap * 8));
             CK(cudaMalloc(&nas, (size_t)ncap * 4));
             const int ld4 = h->ld / 4;
-            const int64_t tot = h->n * ld4;
-            permute_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(
-                reinterpret_cast<const float4*>(h->rows), reinterpret_cast<float4*>(nrows), h->perm, h->n, ld4);
+            const int64_t tot = n * ld4;
+            permute_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+                reinterpret_cast<const float4*>(h->rows), reinterpret_cast<float4*>(nrows), src, n, ld4);
             CK(cudaGetLastError());
-            permute_ids_kernel<<<(unsigned)((h->n + 255) / 256), 256, 0, h->stream>>>(h->ids, nids, h->assign, nas, h->perm, h->n);
+            permute_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->assign, nas, src, n);
             CK(cudaGetLastError());
             h->launches += 2;
-            CK(cudaStreamSynchronize(h->stream));
+            CK(cudaStreamSynchronize(st));
             cudaFree(h->rows);
-            cudaFree(h->ids);
             cudaFree(h->assign);
             h->rows = nrows;
-            h->ids = nids;
             h->assign = nas;
+            if (ncap > h->cap) {  // ids keep their insertion order; they only follow the capacity
+                int64_t* nids = nullptr;
+                CK(cudaMalloc(&nids, (size_t)ncap * 8));
+                CK(cudaMemcpy(nids, h->ids, (size_t)n * 8, cudaMemcpyDeviceToDevice));
+                cudaFree(h->ids);
+                h->ids = nids;
+            }
             h->cap = ncap;
-            h->contiguous = true;
+            cudaFree(h->row_pos);
+            h->row_pos = pos_out;  // storage row -> insertion position
+            h->map_cap = mcap;
+            pos_out = nullptr;
+            cudaFree(src);
+            src = nullptr;
+            grouped = true;
         }
+    }
+    if (!grouped) {  // rows stay put: lists are row indices, row_pos (if any) still describes the storage
+        CK(cudaStreamSynchronize(st));
+        h->slot_row = src;
+        cudaFree(pos_out);
     }
     h->csr_dirty = false;
     return 0;
@@ -949,8 +1058,8 @@ static int ensure_csr(wb_index* h) {
 // ---- add -----------------------------------------------------------------------------------
 // assign rows [n0, n0+n) of the store to their max-inner-product centroid (K4 with k = 1)
 static int assign_rows(wb_index* h, const float* x_dev, int64_t n, int32_t* assign_out, float* best_out,
-                       cudaStream_t st) {
-    if (assign_gemm_eligible(h, n)) return run_assign_gemm(h, x_dev, n, assign_out, best_out, st);
+                       cudaStream_t st, bool tf32 = false) {
+    if (assign_gemm_eligible(h, n)) return run_assign_gemm(h, x_dev, n, assign_out, best_out, st, tf32);
     TRY(h->pD.ensure((size_t)n * sizeof(float)));
     TRY(h->pI.ensure((size_t)n * sizeof(int64_t)));
     float* D = best_out ? best_out : h->pD.as<float>();
@@ -962,13 +1071,14 @@ static int assign_rows(wb_index* h, const float* x_dev, int64_t n, int32_t* assi
 }
 
 static int add_common(wb_index* h, int64_t n, const float* x, const int64_t* ids, bool host, const int32_t* preassign,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool sync_host = true) {
     if (!h) return fail("NULL index");
     if (n < 0) return fail("negative n");
     if (n == 0) return 0;
     if (!x) return fail("x is NULL");
     TRY(set_dev(h));
     if (h->ivf && !h->trained) return fail("IndexIVFFlat must be trained before adding vectors");
+    if (h->n + n > h->cap && st != h->stream) CK(cudaStreamSynchronize(st));  // growth copies run on the handle's stream
     TRY(ensure_capacity(h, h->n + n));
     const int64_t n0 = h->n;
     float* dst = h->rows + (size_t)n0 * h->ld;
@@ -1000,6 +1110,11 @@ static int add_common(wb_index* h, int64_t n, const float* x, const int64_t* ids
         CK(cudaGetLastError());
         h->launches++;
     }
+    if (h->row_pos) {  // the store has been grouped before: new rows sit at their insertion position
+        iota_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->row_pos, n0, n);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
     if (h->ivf) {
         if (preassign) {
             CK(cudaMemcpyAsync(h->assign + n0, preassign, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -1009,13 +1124,54 @@ static int add_common(wb_index* h, int64_t n, const float* x, const int64_t* ids
         h->csr_dirty = true;
     }
     h->n += n;
-    if (host) CK(cudaStreamSynchronize(st));  // the caller may reuse its buffers on return
+    if (host && sync_host) CK(cudaStreamSynchronize(st));  // the caller may reuse its buffers on return
     return 0;
 }
 
 extern "C" int wb_add_with_ids(wb_index* h, int64_t n, const float* x_host, const int64_t* ids_host) {
     return add_common(h, n, x_host, ids_host, true, nullptr, h ? h->stream : nullptr);
 }
+// ---- pinned, overlapped ingest (FeatureStore shards -> HBM) ------------------------------------------------------
+// The loader decodes shard i+1 into one pinned buffer while the copy engine moves shard i out of another and the
+// SMs assign its rows to their lists: wb_add_with_ids_pinned enqueues (H2D, norms, ids, IVF assignment) on the
+// handle's stream and returns at once; `slot` names the pinned buffer, wb_add_slot_wait(slot) blocks until the GPU has
+// finished reading it.  Replaces the synchronous per-batch add of feature_search_index.py:79-82.
+extern "C" int wb_pinned_alloc(int64_t bytes, void** out) {
+    if (!out || bytes <= 0) return fail("bad arguments");
+    *out = nullptr;
+    CK(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return 0;
+}
+extern "C" int wb_pinned_free(void* p) {
+    if (p) CK(cudaFreeHost(p));
+    return 0;
+}
+extern "C" int wb_add_with_ids_pinned(wb_index* h, int64_t n, const float* x_pinned, const int64_t* ids_pinned, int slot) {
+    if (!h) return fail("NULL index");
+    if (slot < 0 || slot >= wb_index::kAddSlots) return fail("slot %d out of range [0, %d)", slot, wb_index::kAddSlots);
+    TRY(set_dev(h));
+    if (!h->add_ev[slot]) CK(cudaEventCreateWithFlags(&h->add_ev[slot], cudaEventDisableTiming));
+    TRY(add_common(h, n, x_pinned, ids_pinned, true, nullptr, h->stream, false));
+    CK(cudaEventRecord(h->add_ev[slot], h->stream));
+    h->add_pending[slot] = true;
+    return 0;
+}
+extern "C" int wb_add_slot_wait(wb_index* h, int slot) {
+    if (!h) return fail("NULL index");
+    if (slot < 0 || slot >= wb_index::kAddSlots) return fail("slot %d out of range [0, %d)", slot, wb_index::kAddSlots);
+    if (!h->add_pending[slot]) return 0;
+    TRY(set_dev(h));
+    CK(cudaEventSynchronize(h->add_ev[slot]));
+    h->add_pending[slot] = false;
+    return 0;
+}
+extern "C" int wb_sync(wb_index* h) {
+    if (!h) return fail("NULL index");
+    TRY(set_dev(h));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 extern "C" int wb_add_with_ids_dev(wb_index* h, int64_t n, const float* x_dev, const int64_t* ids_dev, void* stream) {
     return add_common(h, n, x_dev, ids_dev, false, nullptr, (cudaStream_t)stream);
 }
@@ -1052,7 +1208,8 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
     p.ld = h->ld;
     p.k = (int)k;
     p.nparts = (int)S;
-    p.perm = h->contiguous ? nullptr : h->perm;
+    p.perm = h->slot_row;
+    p.row_pos = h->row_pos;
     p.list_off = h->list_off;
     p.nprobe = np;
     if (ex && nq > kMaxGridY) ex = nullptr;
@@ -1197,6 +1354,27 @@ extern "C" int wb_merge_topk_dev(int device, int64_t nq, int64_t k, int64_t npar
     return 0;
 }
 
+// ---- IVF: make the inverted lists current (K8) and describe them ---------------------------------------------------
+// faiss keeps its inverted lists current on every add; this backend groups the row store lazily, at the first search
+// after an add.  write_index calls this first so that every list is one contiguous run of storage rows.
+extern "C" int wb_ivf_finalize(wb_index* h) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    TRY(set_dev(h));
+    return ensure_csr(h);
+}
+// list_off_host[nlist + 1]: list l holds the storage rows [list_off[l], list_off[l+1]) once wb_ivf_finalize has run
+// and *grouped_out is 1 (0: the rows could not be regrouped for lack of memory; use wb_export_rows + assignments).
+extern "C" int wb_ivf_list_offsets(wb_index* h, int64_t* list_off_host, int* grouped_out) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    if (!list_off_host) return fail("NULL buffer");
+    TRY(set_dev(h));
+    TRY(ensure_csr(h));
+    CK(cudaMemcpyAsync(list_off_host, h->list_off, (size_t)(h->nlist + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (grouped_out) *grouped_out = h->slot_row == nullptr;
+    return 0;
+}
+
 // ---- row access ----------------------------------------------------------------------------
 extern "C" int wb_reconstruct_batch(wb_index* h, int64_t m, const int64_t* ids_host, float* out_host) {
     if (!h) return fail("NULL index");
@@ -1214,7 +1392,7 @@ extern "C" int wb_reconstruct_batch(wb_index* h, int64_t m, const int64_t* ids_h
     for (int64_t j0 = 0; j0 < m; j0 += 64) {
         const int mm = (int)std::min<int64_t>(64, m - j0);
         const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>((h->n + 255) / 256, 1), h->sm_count * 8);
-        find_ids_kernel<<<grid, 256, 0, st>>>(h->ids, h->n, tgt + j0, mm, pos + j0);
+        find_ids_kernel<int64_t><<<grid, 256, 0, st>>>(h->ids, h->n, tgt + j0, mm, pos + j0);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -1223,6 +1401,17 @@ extern "C" int wb_reconstruct_batch(wb_index* h, int64_t m, const int64_t* ids_h
     CK(cudaStreamSynchronize(st));
     for (int64_t j = 0; j < m; ++j)
         if (hpos[j] < 0) return fail("reconstruct: id %lld not found in the index", (long long)ids_host[j]);
+    if (h->row_pos) {  // grouped IVF store: insertion position -> storage row
+        CK(cudaMemcpyAsync(tgt, pos, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemsetAsync(pos, 0xFF, (size_t)m * sizeof(int64_t), st));
+        for (int64_t j0 = 0; j0 < m; j0 += 64) {
+            const int mm = (int)std::min<int64_t>(64, m - j0);
+            const unsigned grid = (unsigned)std::min<int64_t>(std::max<int64_t>((h->n + 255) / 256, 1), h->sm_count * 8);
+            find_ids_kernel<uint32_t><<<grid, 256, 0, st>>>(h->row_pos, h->n, tgt + j0, mm, pos + j0);
+            CK(cudaGetLastError());
+            h->launches++;
+        }
+    }
     const int64_t tot = m * h->d;
     gather_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->rows, h->ld, h->d, (const int64_t*)pos, m,
                                                                        h->xbuf.as<float>());
@@ -1244,7 +1433,17 @@ extern "C" int wb_export_rows(wb_index* h, int64_t start, int64_t n, float* x_ho
     if (x_host)
         CK(cudaMemcpy2DAsync(x_host, (size_t)h->d * 4, h->rows + (size_t)start * h->ld, (size_t)h->ld * 4,
                              (size_t)h->d * 4, (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (ids_host) CK(cudaMemcpyAsync(ids_host, h->ids + start, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (ids_host) {
+        if (h->row_pos) {  // grouped IVF store: the id of storage row r is ids[row_pos[r]]
+            TRY(h->idbuf.ensure((size_t)n * 8));
+            gather_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->ids, h->row_pos, start, n, h->idbuf.as<int64_t>());
+            CK(cudaGetLastError());
+            h->launches++;
+            CK(cudaMemcpyAsync(ids_host, h->idbuf.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        } else {
+            CK(cudaMemcpyAsync(ids_host, h->ids + start, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        }
+    }
     if (assign_host) {
         if (!h->ivf) return fail("assignments exist only for IVF indices");
         CK(cudaMemcpyAsync(assign_host, h->assign + start, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -1264,6 +1463,15 @@ extern "C" int wb_ivf_set_centroids(wb_index* h, const float* c) {
                          cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->trained = true;
+    return 0;
+}
+
+// faiss ClusteringParameters::spherical.  Default 0: an IndexIVFFlat built with the plain constructor, as the
+// reference does (feature_search_index.py:60), trains with spherical = false [faiss-upstream]; index_factory is what
+// switches it on for inner-product indices.
+extern "C" int wb_ivf_set_spherical(wb_index* h, int on) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    h->spherical = on != 0;
     return 0;
 }
 
@@ -1298,8 +1506,19 @@ static int stage_points(wb_index* h, int64_t n, const float* x_dev, cudaStream_t
     return 0;
 }
 
+static int kmeans_assign_impl(wb_index* h, int64_t n, const float* x_dev, int32_t* assign_dev, double* objective_host,
+                              void* stream, bool tf32);
 extern "C" int wb_kmeans_assign_dev(wb_index* h, int64_t n, const float* x_dev, int32_t* assign_dev,
                                     double* objective_host, void* stream) {
+    return kmeans_assign_impl(h, n, x_dev, assign_dev, objective_host, stream, false);
+}
+// TRAINING-only variant: plain-TF32 scores (one tensor-core term instead of three), ~3x less tensor work.
+extern "C" int wb_kmeans_assign_fast_dev(wb_index* h, int64_t n, const float* x_dev, int32_t* assign_dev,
+                                         double* objective_host, void* stream) {
+    return kmeans_assign_impl(h, n, x_dev, assign_dev, objective_host, stream, env_int("WB_KMEANS_EXACT", 0) == 0);
+}
+static int kmeans_assign_impl(wb_index* h, int64_t n, const float* x_dev, int32_t* assign_dev, double* objective_host,
+                              void* stream, bool tf32) {
     if (!h || !h->ivf) return fail("not an IVF index");
     if (n <= 0 || !x_dev || !assign_dev) return fail("bad arguments");
     TRY(set_dev(h));
@@ -1307,7 +1526,7 @@ extern "C" int wb_kmeans_assign_dev(wb_index* h, int64_t n, const float* x_dev, 
     const float* x = nullptr;
     TRY(stage_points(h, n, x_dev, st, &x));
     TRY(h->dbuf.ensure((size_t)n * sizeof(float)));
-    TRY(assign_rows(h, x, n, assign_dev, h->dbuf.as<float>(), st));
+    TRY(assign_rows(h, x, n, assign_dev, h->dbuf.as<float>(), st, tf32));
     if (objective_host) {
         TRY(h->misc.ensure(sizeof(double)));
         CK(cudaMemsetAsync(h->misc.p, 0, sizeof(double), st));
@@ -1327,18 +1546,15 @@ extern "C" int wb_kmeans_accumulate_dev(wb_index* h, int64_t n, const float* x_d
     if (n < 0 || !sums_dev || !counts_dev) return fail("bad arguments");
     TRY(set_dev(h));
     cudaStream_t st = (cudaStream_t)stream;
-    std::vector<uint32_t> perm;
-    std::vector<int64_t> off;
-    TRY(build_csr_host(assign_dev, n, h->nlist, perm, off, st));
     TRY(h->kperm.ensure(std::max<size_t>((size_t)n * 4, 16)));
     TRY(h->koff.ensure((size_t)(h->nlist + 1) * 8));
-    if (n) CK(cudaMemcpyAsync(h->kperm.p, perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->koff.p, off.data(), (size_t)(h->nlist + 1) * 8, cudaMemcpyHostToDevice, st));
+    // group the points by their centroid on the device (stable: every list is summed in insertion order, so the
+    // result does not depend on the schedule); no host copy, no synchronisation
+    TRY(device_csr(h, assign_dev, n, nullptr, h->koff.as<int64_t>(), h->kperm.as<uint32_t>(), nullptr, st, false));
     segment_sum_kernel<<<(unsigned)h->nlist, 256, 0, st>>>(x_dev, h->d, h->d, h->kperm.as<uint32_t>(),
                                                           h->koff.as<int64_t>(), sums_dev, counts_dev);
     CK(cudaGetLastError());
     h->launches++;
-    CK(cudaStreamSynchronize(st));  // perm/off host vectors die here
     return 0;
 }
 
@@ -1396,9 +1612,11 @@ extern "C" int wb_kmeans_update_dev(wb_index* h, const float* sums_dev, const in
         CK(cudaMemcpyAsync(h->centroids, cen.data(), (size_t)k * ld * 4, cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));
     }
-    renorm_rows_kernel<<<(unsigned)k, 256, 0, st>>>(h->centroids, ld, d);
-    CK(cudaGetLastError());
-    h->launches++;
+    if (h->spherical) {
+        renorm_rows_kernel<<<(unsigned)k, 256, 0, st>>>(h->centroids, ld, d);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
     if (nsplit_host) *nsplit_host = nsplit;
     return 0;
 }
@@ -1433,15 +1651,26 @@ extern "C" int wb_ivf_train(wb_index* h, int64_t n, const float* x_host, int nit
             std::swap(perm[i], perm[i2]);
         }
         if ((rc = (cudaMemsetAsync(h->centroids, 0, (size_t)k * h->ld * 4, st) != cudaSuccess))) break;
-        for (int64_t c = 0; c < k && !rc; ++c)
-            rc = cudaMemcpyAsync(h->centroids + (size_t)c * h->ld, x + (size_t)perm[c] * d, (size_t)d * 4,
-                                 cudaMemcpyDeviceToDevice, st) != cudaSuccess;
-        if (rc) break;
-        renorm_rows_kernel<<<(unsigned)k, 256, 0, st>>>(h->centroids, h->ld, d);
-        h->launches++;
+        {   // the k picked rows, gathered by one kernel
+            if ((rc = h->idbuf.ensure((size_t)k * 8))) break;
+            if ((rc = (cudaMemcpyAsync(h->idbuf.p, perm.data(), (size_t)k * 8, cudaMemcpyHostToDevice, st) != cudaSuccess))) break;
+            if (h->ld == d) {
+                gather_rows_kernel<<<(unsigned)((k * d + 255) / 256), 256, 0, st>>>(x, d, d, h->idbuf.as<int64_t>(), k, h->centroids);
+            } else {
+                if ((rc = h->xbuf.ensure((size_t)k * d * 4))) break;
+                gather_rows_kernel<<<(unsigned)((k * d + 255) / 256), 256, 0, st>>>(x, d, d, h->idbuf.as<int64_t>(), k, h->xbuf.as<float>());
+                pad_rows_kernel<<<(unsigned)((k * h->ld + 255) / 256), 256, 0, st>>>(h->xbuf.as<float>(), h->centroids, k, d, h->ld);
+            }
+            h->launches++;
+            if ((rc = (cudaStreamSynchronize(st) != cudaSuccess))) break;  // perm (host) is read by the copy above
+        }
+        if (h->spherical) {
+            renorm_rows_kernel<<<(unsigned)k, 256, 0, st>>>(h->centroids, h->ld, d);
+            h->launches++;
+        }
         for (int it = 0; it < niter && !rc; ++it) {
             double obj = 0;
-            if ((rc = wb_kmeans_assign_dev(h, n, x, assign, &obj, st))) break;
+            if ((rc = wb_kmeans_assign_fast_dev(h, n, x, assign, &obj, st))) break;
             if ((rc = wb_kmeans_accumulate_dev(h, n, x, assign, sums, counts, st))) break;
             int64_t nsplit = 0;
             if ((rc = wb_kmeans_update_dev(h, sums, counts, n, 1234, &nsplit, st))) break;

@@ -76,7 +76,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
            (2ull << 61);
 }
 
-template <bool TIMING_ONLY = false>
+// ARGMAX (k-means TRAINING assignment, K6): rows = points, "queries" = centroids in 256-wide blocks; a pair walks
+// all centroid blocks of its row tiles back to back and every row keeps a running (max, lowest index) in the
+// epilogue registers - plain TF32 scores (SURVEY.md 8d allows it for training: "argmax only"), so two centroids
+// whose scores differ by less than ~2e-3 |x||c| may swap.  Add-time assignment stays on the exact 3xTF32 kernel.
+template <bool ARGMAX = false, bool TIMING_ONLY = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF2Threads, 1)
 filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_f2[];
@@ -96,13 +100,22 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
     const int64_t ntiles = (p.row_end - p.row_begin + kGemmBM - 1) / kGemmBM;
     const int64_t ntp = (ntiles + 1) / 2;  // tile pairs
     const int64_t nwork = ntp * p.nqb;
-    const int64_t my_work = nwork > pair ? (nwork - pair + npairs - 1) / npairs : 0;
-    // (tile pair, query block) items are interleaved over the pairs: neighbouring pairs work on the same rows with
-    // different query blocks at the same time, so only the first of them misses L2
+    const int64_t my_tp = ntp > pair ? (ntp - pair + npairs - 1) / npairs : 0;
+    const int64_t my_work = ARGMAX ? my_tp * p.nqb : (nwork > pair ? (nwork - pair + npairs - 1) / npairs : 0);
+    // search: (tile pair, query block) items are interleaved over the pairs - neighbouring pairs work on the same rows
+    // with different query blocks at the same time, so only the first of them misses L2.  ARGMAX: a pair owns whole
+    // tile pairs and walks every centroid block of one before it moves on (the running maximum lives in registers).
     auto work_at = [&](int64_t it, int64_t& tile, int& qb) {  // tile = THIS CTA's row tile
-        const int64_t w = pair + it * npairs;
-        const int64_t tp = w / p.nqb;
-        qb = (int)(w - tp * p.nqb);
+        int64_t tp;
+        if (ARGMAX) {
+            const int64_t t = it / p.nqb;
+            tp = pair + t * npairs;
+            qb = (int)(it - t * p.nqb);
+        } else {
+            const int64_t w = pair + it * npairs;
+            tp = w / p.nqb;
+            qb = (int)(w - tp * p.nqb);
+        }
         tile = 2 * tp + crank;
     };
 
@@ -207,14 +220,21 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
         const int etid = tid - 4 * 32;      // 0..255
         int buf = 0;
         uint32_t dph = 0;
+        float best = -INFINITY;  // ARGMAX: running maximum of this thread's row over its half of every centroid block
+        int best_i = 0;
         for (int64_t it = 0; it < my_work; ++it) {
             int64_t tile;
             int qb;
             work_at(it, tile, qb);
             const int64_t row = p.row_begin + tile * kGemmBM + quarter * 32 + lane;
             const bool row_ok = row < p.row_end;
-            thr_s[buf * kF2BN + etid] = p.thr[qb * kF2BN + etid] - p.margin[qb * kF2BN + etid];  // +inf for padding
-            named_bar_sync(kBarEpilogue, kF2EpiThreads);
+            if constexpr (!ARGMAX) {
+                thr_s[buf * kF2BN + etid] = p.thr[qb * kF2BN + etid] - p.margin[qb * kF2BN + etid];  // +inf for padding
+                named_bar_sync(kBarEpilogue, kF2EpiThreads);
+            } else if (qb == 0) {
+                best = -INFINITY;
+                best_i = 0;
+            }
             mbar_wait(&d_full[buf], dph);
             tc_fence_after();
             const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kF2BN + chalf * kF2Half);
@@ -225,6 +245,20 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
                 tmem_ld32(td + cb * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if constexpr (TIMING_ONLY) continue;
+                if constexpr (ARGMAX) {
+                    const int c0 = qb * kF2BN + chalf * kF2Half + cb * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __uint_as_float(v[j]);
+                        // ascending index order + strict '>' keeps the lowest index on ties; padded columns
+                        // (index >= nq) hold zeros and must not win
+                        if (c0 + j < p.nq && sc > best) {
+                            best = sc;
+                            best_i = c0 + j;
+                        }
+                    }
+                    continue;
+                }
                 // almost nothing passes: one vote per 32 columns, the per-column path only when something did
                 bool any = false;
 #pragma unroll
@@ -257,7 +291,29 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&d_empty[buf], 0);
-            named_bar_sync(kBarEpilogue, kF2EpiThreads);  // thr_s[buf] may be rewritten two tiles later
+            if constexpr (!ARGMAX) {
+                named_bar_sync(kBarEpilogue, kF2EpiThreads);  // thr_s[buf] may be rewritten two tiles later
+            } else if (qb == p.nqb - 1) {
+                // the two warps of a row quarter hold the maxima of the two column halves: combine through thr_s
+                float* cb_s = thr_s;                                   // [128] best score of the upper half
+                int* ci_s = reinterpret_cast<int*>(thr_s + kGemmBM);   // [128] its index
+                if (chalf == 1) {
+                    cb_s[quarter * 32 + lane] = best;
+                    ci_s[quarter * 32 + lane] = best_i;
+                }
+                named_bar_sync(kBarEpilogue, kF2EpiThreads);
+                if (chalf == 0 && row_ok) {
+                    const float b1 = cb_s[quarter * 32 + lane];
+                    const int i1 = ci_s[quarter * 32 + lane];
+                    if (b1 > best || (b1 == best && i1 < best_i)) {
+                        best = b1;
+                        best_i = i1;
+                    }
+                    p.assign_out[row] = best_i;
+                    if (p.best_out) p.best_out[row] = best;
+                }
+                named_bar_sync(kBarEpilogue, kF2EpiThreads);  // cb_s / ci_s are rewritten at the next tile
+            }
             if (++buf == 2) { buf = 0; dph ^= 1u; }
         }
     }

@@ -342,13 +342,21 @@ __global__ void permute_rows_kernel(const float4* src, float4* dst, const uint32
         dst[i] = src[(size_t)perm[r] * ld4 + c];
     }
 }
-__global__ void permute_ids_kernel(const int64_t* ids, int64_t* ids_out, const int32_t* asg, int32_t* asg_out,
-                                   const uint32_t* perm, int64_t n) {
+// out[i] = in[src[i]] (IVF re-grouping: list assignment of each moved row)
+__global__ void permute_i32_kernel(const int32_t* in, int32_t* out, const uint32_t* src, int64_t n) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) {
-        ids_out[i] = ids[perm[i]];
-        asg_out[i] = asg[perm[i]];
-    }
+    if (i < n) out[i] = in[src[i]];
+}
+
+// out[i] = ids[pos ? pos[start + i] : start + i]: external ids of the storage rows [start, start + n)
+__global__ void gather_ids_kernel(const int64_t* ids, const uint32_t* pos, int64_t start, int64_t n, int64_t* out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ids[pos ? (int64_t)pos[start + i] : start + i];
+}
+
+__global__ void iota_u32_kernel(uint32_t* v, int64_t start, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) v[start + i] = (uint32_t)(start + i);
 }
 
 // out[m, d] <- rows[pos[m], 0:d]
@@ -361,14 +369,14 @@ __global__ void gather_rows_kernel(const float* rows, int ld, int d, const int64
     }
 }
 
-// pos[j] = lowest position whose id equals targets[j] (-1 if none); m <= 64 per launch
-__global__ void find_ids_kernel(const int64_t* ids, int64_t n, const int64_t* targets, int m,
-                                unsigned long long* pos) {
+// pos[j] = lowest position whose value equals targets[j] (-1 if none); m <= 64 per launch
+template <class T>
+__global__ void find_ids_kernel(const T* ids, int64_t n, const int64_t* targets, int m, unsigned long long* pos) {
     __shared__ int64_t t[64];
     if (threadIdx.x < m) t[threadIdx.x] = targets[threadIdx.x];
     __syncthreads();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t v = ids[i];
+        const int64_t v = (int64_t)ids[i];
         for (int j = 0; j < m; ++j)
             if (v == t[j]) atomicMin(&pos[j], (unsigned long long)i);
     }

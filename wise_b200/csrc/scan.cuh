@@ -50,6 +50,7 @@ struct ScanParams {
     int nparts;             // == gridDim.x
     // gather mode (IVF): candidates = concatenation of the probed lists of query blockIdx.y
     const uint32_t* perm;     // CSR: row index per slot; null when the rows are physically grouped by list
+    const uint32_t* row_pos;  // storage row -> insertion position (the tie rule and the id lookup); null: identity
     const int64_t* list_off;  // CSR: [nlist + 1]
     const int64_t* probes;    // [nq][nprobe] list ids (-1 = none)
     int nprobe;
@@ -311,7 +312,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             if (owner) {
                 const int64_t cpos = g * kGroupRows + cw * kRowsPerWarp + r;
                 if (cpos < total && score >= thr_s[b]) {
-                    const uint32_t pos = GATHER ? gather_row(G, (uint32_t)cpos) : (uint32_t)cpos;
+                    uint32_t pos = GATHER ? gather_row(G, (uint32_t)cpos) : (uint32_t)cpos;
+                    if (GATHER && p.row_pos) pos = p.row_pos[pos];  // grouped store: ties go by INSERTION position
                     const uint64_t key = make_key(score, pos);
                     if (key > lists[(size_t)b * P + k - 1]) {
                         const int slot = atomicAdd(&qcnt[b], 1);

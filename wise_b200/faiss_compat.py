@@ -139,9 +139,10 @@ class Index:
         return D, I
 
     # -- bulk access used by write_index --------------------------------------------------------
-    def _export(self, start: int, n: int, want_assign: bool = False):
+    def _export(self, start: int, n: int, want_assign: bool = False, want_ids: bool = True):
+        """Storage rows [start, start+n): insertion order for flat indices, list by list for a finalized IVF index."""
         x = np.empty((n, self.d), np.float32)
-        ids = np.empty((n,), np.int64)
+        ids = np.empty((n,), np.int64) if want_ids else None
         a = np.empty((n,), np.int32) if want_assign else None
         _capi.check(_capi.lib().wb_export_rows(self._h, start, n, _capi.ptr(x), _capi.ptr(ids), _capi.ptr(a)))
         return x, ids, a
@@ -194,6 +195,19 @@ class DirectMap:
         self.type = DirectMap.NoMap
 
 
+class ClusteringParameters:
+    """faiss.ClusteringParameters as IndexIVF.cp holds it [faiss-upstream defaults for IndexIVFFlat built with the
+    plain constructor, /root/reference/src/index/feature_search_index.py:60]: niter 10 (Level1Quantizer), seed 1234,
+    spherical False (only index_factory switches it on for inner-product indices), 39..256 points per centroid."""
+
+    def __init__(self):
+        self.niter = _KMEANS_NITER_IVF
+        self.seed = _KMEANS_SEED
+        self.spherical = False
+        self.min_points_per_centroid = _MIN_POINTS_PER_CENTROID
+        self.max_points_per_centroid = _MAX_POINTS_PER_CENTROID
+
+
 class IndexIVFFlat(Index):
     """faiss.IndexIVFFlat(quantizer, d, nlist, METRIC_INNER_PRODUCT)
     (/root/reference/src/index/feature_search_index.py:60)."""
@@ -210,6 +224,7 @@ class IndexIVFFlat(Index):
         self.parallel_mode = 0  # accepted and ignored: the GPU always fans one query over all probed lists
         self.quantizer = quantizer
         self.direct_map = DirectMap()
+        self.cp = ClusteringParameters()
         self._device = quantizer._device if quantizer is not None else default_device()
         h = C.c_void_p()
         _capi.check(_capi.lib().wb_ivf_create(self.d, self.nlist, self._device, C.byref(h)))
@@ -219,16 +234,26 @@ class IndexIVFFlat(Index):
         return max(1, int(self.nprobe))
 
     def train(self, x) -> None:
-        """index.train(train_features) (/root/reference/src/index/feature_search_index.py:75):
-        spherical k-means, faiss Clustering defaults (niter=10, seed=1234, <=256 points/centroid)."""
+        """index.train(train_features) (/root/reference/src/index/feature_search_index.py:75): k-means with
+        max-inner-product assignment, faiss Clustering defaults in self.cp (niter=10, seed=1234, spherical=False,
+        at most 256 training points per centroid: a larger set is subsampled, a set below 39 per centroid warns)."""
         x = _as_f32_matrix(x, self.d, "x")
         if self.is_trained:
             return  # faiss: "IVF quantizer does not need training"
         n = x.shape[0]
-        if n < self.nlist * _MIN_POINTS_PER_CENTROID:
+        cp = self.cp
+        if n > self.nlist * cp.max_points_per_centroid:  # faiss Clustering::train subsamples [faiss-upstream]
+            keep = self.nlist * cp.max_points_per_centroid
+            print(f"Sampling a subset of {keep} / {n} for training", file=sys.stderr)
+            sel = np.random.RandomState(cp.seed).permutation(n)[:keep]
+            x = np.ascontiguousarray(x[sel])
+            n = keep
+        elif n < self.nlist * cp.min_points_per_centroid:
             print(f"WARNING clustering {n} points to {self.nlist} centroids: please provide at least "
-                  f"{self.nlist * _MIN_POINTS_PER_CENTROID} training points", file=sys.stderr)
-        _capi.check(_capi.lib().wb_ivf_train(self._h, n, _capi.ptr(x), _KMEANS_NITER_IVF, _KMEANS_SEED))
+                  f"{self.nlist * cp.min_points_per_centroid} training points", file=sys.stderr)
+        L = _capi.lib()
+        _capi.check(L.wb_ivf_set_spherical(self._h, int(bool(cp.spherical))))
+        _capi.check(L.wb_ivf_train(self._h, n, _capi.ptr(x), int(cp.niter), int(cp.seed)))
         self._sync_quantizer()
 
     def _sync_quantizer(self) -> None:

@@ -104,6 +104,12 @@ def write_index(index, fname: str) -> None:
 
 def _write_ivf(f, index) -> None:
     n, d, nlist = index.ntotal, index.d, index.nlist
+    if n and index.is_trained:
+        # group the row store list by list first (K8 on the device): every inverted list is then ONE contiguous run of
+        # storage rows and is exported with one copy per chunk.  Without it (train, add, write - no search in between,
+        # which is exactly /root/reference/src/index/feature_search_index.py:75-84) the rows are still in insertion order
+        # and a list would be gathered row by row.
+        _capi.check(_capi.lib().wb_ivf_finalize(index._h))
     f.write(b"IwFl")
     _hdr(f, d, n, index.is_trained, fc.METRIC_INNER_PRODUCT)
     f.write(struct.pack("<QQ", nlist, int(index.nprobe)))
@@ -164,7 +170,7 @@ def _gather_rows(index, rows: np.ndarray) -> np.ndarray:
     starts = np.concatenate([[0], breaks])
     ends = np.concatenate([breaks, [rows.size]])
     for s, e in zip(starts, ends):
-        x, _, _ = index._export(int(rows[s]), int(e - s))
+        x, _, _ = index._export(int(rows[s]), int(e - s), want_ids=False)
         out[s:e] = x
     return out
 

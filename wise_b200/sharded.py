@@ -188,8 +188,8 @@ def train_ivf_sharded(index, x_local: torch.Tensor, niter: int = 10, seed: int =
     """index.train() with the training rows sharded over the ranks: every rank assigns and
     accumulates ITS rows (K6/K7 on its GPU), one all-reduce of [nlist*d sums | nlist counts] per iteration,
     then every rank applies the identical centroid update, so the centroids stay replicated bit for bit.
-    Mirrors faiss Clustering::train for IndexIVFFlat(METRIC_INNER_PRODUCT): spherical, niter=10, seed=1234,
-    initial centroids = k random training rows.  `index` is this rank's (empty, untrained) IndexIVFFlat;
+    Mirrors faiss Clustering::train for IndexIVFFlat(METRIC_INNER_PRODUCT): index.cp.spherical (default False, like
+    the reference's plain-constructor index), niter=10, seed=1234, initial centroids = k random training rows.  `index` is this rank's (empty, untrained) IndexIVFFlat;
     x_local is a float32 [n_local, d] CUDA tensor.  Returns the objective (sum of max inner products) per iteration."""
     import ctypes as C
     from . import _capi
@@ -217,7 +217,10 @@ def train_ivf_sharded(index, x_local: torch.Tensor, niter: int = 10, seed: int =
     init[mine.nonzero().squeeze(1).to(dev)] = x_local[(pick[mine] - lo).to(dev)]
     if world > 1:
         dist.all_reduce(init, group=group)
-    init = torch.nn.functional.normalize(init, dim=1)
+    spherical = bool(getattr(getattr(index, "cp", None), "spherical", False))
+    if spherical:
+        init = torch.nn.functional.normalize(init, dim=1)
+    _capi.check(L.wb_ivf_set_spherical(index._h, int(spherical)))
     init_h = np.ascontiguousarray(init.cpu().numpy())  # keep a reference: the C call borrows this buffer
     _capi.check(L.wb_ivf_set_centroids(index._h, _capi.ptr(init_h)))
     st = torch.cuda.current_stream(dev).cuda_stream
@@ -227,7 +230,7 @@ def train_ivf_sharded(index, x_local: torch.Tensor, niter: int = 10, seed: int =
     objs = []
     for it in range(niter):
         obj = C.c_double(0)
-        _capi.check(L.wb_kmeans_assign_dev(index._h, n_local, x_local.data_ptr(), assign.data_ptr(), C.byref(obj), st))
+        _capi.check(L.wb_kmeans_assign_fast_dev(index._h, n_local, x_local.data_ptr(), assign.data_ptr(), C.byref(obj), st))
         _capi.check(L.wb_kmeans_accumulate_dev(index._h, n_local, x_local.data_ptr(), assign.data_ptr(), sums.data_ptr(),
                                                cnts.data_ptr(), st))
         o = torch.tensor([obj.value], dtype=torch.float64, device=dev)
