@@ -106,3 +106,35 @@ def test_feature_search_index_recipe(faiss, tmp_path, index_type):
     qv = RandomFeatures("x").extract_text_features(["This is a photo of a cooking"])
     Dr, Ir = O.flat_search(x, qv, 20, np.arange(1, n + 1))
     O.compare_topk(dist[None], ids[None], Dr, Ir)
+
+
+def test_pipelined_ingest_equals_batch_loop(faiss, tmp_path, monkeypatch):
+    """Shards -> pinned ring -> HBM (wise_b200.ingest, the default of create_index) builds byte-for-byte the same
+    index file as the reference-shaped batch loop (feature_search_index.py:78-82), including a shard the C++ reader
+    must hand to the python reader (a multi-row sample among single-row ones)."""
+    from wise_b200.feature_search_index import FeatureSearchIndex
+    from wise_b200.store import WebdatasetStore
+    feats = tmp_path / "features"
+    feats.mkdir()
+    n, d = 5200, 48
+    x = O.clustered_unit(n, d, 30, 6)
+    w = WebdatasetStore("image", feats)
+    w.enable_write(1000, 1 << 30)
+    i = 0
+    while i < n:
+        if i == 2500:  # one irregular member: 3 rows under one key
+            w.add(i + 1, x[i:i + 3]); i += 3
+        else:
+            w.add(i + 1, x[i:i + 1]); i += 1
+    w.close()
+    files = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("WISE_B200_PIPELINED_INGEST", mode)
+        asset = {"features_dir": feats, "index_dir": tmp_path / ("index" + mode)}
+        si = FeatureSearchIndex("image", "a/b/c/d", asset, feature_extractor_factory=RandomFeatures, verbose=False)
+        si.create_index("IndexFlatIP")
+        files[mode] = si.get_index_filename("IndexFlatIP").read_bytes()
+        assert si.load_index("IndexFlatIP") and si.index.ntotal == n
+    assert files["1"] == files["0"]
+    D, I = si.index.search(x[[0, 2501, n - 1]], 3)
+    assert I[0, 0] == 1 and I[1, 0] == 2501 and I[2, 0] == n  # rows 2500..2502 share key 2501 (one sample of 3 rows)

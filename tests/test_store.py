@@ -30,20 +30,24 @@ def test_reads_reference_written_numpy_store():
     assert bi[0].dtype == np.int64 and bf[0].dtype == np.float32
 
 
-def test_numpy_save_store_round_trip(tmp_path):  # reference test_numpy_save_store
-    w = NumpySaveStore("test-store", tmp_path)
-    w.enable_write(3, -1, verbose=0)
+def test_numpy_save_store_reads_reference_layout(tmp_path):  # reader side of the reference's test_numpy_save_store
+    """Shards in the layout numpy_save_store.py:80-87 writes (feature_id int32[n], features float32[n, d]; the fixture
+    under tests/golden/ is written by the reference's own class): read back sample by sample and in batches."""
     seq = [A, B, Cc, Cc, B, A, B]
-    for i, f in enumerate(seq):
-        w.add(i, f)
-    w.close()
+    for shard, lo in enumerate(range(0, len(seq), 3)):
+        part = seq[lo:lo + 3]
+        np.savez(tmp_path / ("test-store-%06d" % shard), feature_id=np.arange(lo, lo + len(part), dtype=np.int32),
+                 features=np.concatenate(part).astype(np.float32))
     r = NumpySaveStore("test-store", tmp_path)
     r.enable_read()
     loaded = {int(i): v for i, v in r}
     assert r.feature_count == 7 and r.feature_dim == 4
     for i, f in enumerate(seq):
         assert np.all(np.equal(loaded[i], f))
-    assert sorted(os.listdir(tmp_path)) == ["test-store-000000.npz", "test-store-000001.npz", "test-store-000002.npz"]
+    bi, bf = zip(*r.iter_batch(2))
+    assert np.array_equal(np.concatenate(bi), np.arange(7)) and np.array_equal(np.concatenate(bf), np.concatenate(seq))
+    with pytest.raises(NotImplementedError):
+        r.enable_write(3, -1)
 
 
 def test_webdataset_store_batch_write(tmp_path):  # reference test_webdataset_store_batch_write

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import itertools
 import math
+import os
 from pathlib import Path
 
 import numpy as np
@@ -106,7 +107,13 @@ class FeatureSearchIndex(SearchIndex):
             index = faiss.IndexIVFFlat(quantizer, feature_dim, cell_count, faiss.METRIC_INNER_PRODUCT)
             self._say(f"  loading a random sample of {train_count} features from {feature_count} features ...")
             shuffled = type(feature_store)(self.media_type, self.features_dir)
-            shuffled.enable_read(shard_shuffle=True)
+            if isinstance(feature_store, WebdatasetStore) and getattr(feature_store, "_shard_rows", None):
+                # same files: reuse the shard scan instead of walking the store a second time
+                shuffled.shard_shuffle, shuffled.shuffle_values, shuffled.shuffle_bufsize = True, False, 10000
+                shuffled.feature_count, shuffled.feature_dim = feature_count, feature_dim
+                shuffled._shard_rows = dict(feature_store._shard_rows)
+            else:
+                shuffled.enable_read(shard_shuffle=True)
             train_features = np.ndarray((train_count, feature_dim), dtype=np.float32)
             if isinstance(shuffled, WebdatasetStore):
                 # same sample as the reference's islice over the shard-shuffled stream (:66-71), read shard-wise
@@ -128,11 +135,17 @@ class FeatureSearchIndex(SearchIndex):
 
         self._say("Adding feature vectors to index")
         index.reserve(feature_count)
-        # the reference adds 512 rows per call (iter_batch default); larger batches amortise the call overhead
-        batches = (feature_store.iter_batch(batch_size=65536, exact=False) if isinstance(feature_store, WebdatasetStore)
-                   else feature_store.iter_batch(batch_size=65536))
-        for ids_batch, vectors_batch in batches:
-            index.add_with_ids(np.ascontiguousarray(vectors_batch, np.float32), np.ascontiguousarray(ids_batch, np.int64))
+        if (isinstance(feature_store, WebdatasetStore) and getattr(feature_store, "_shard_rows", None)
+                and os.environ.get("WISE_B200_PIPELINED_INGEST", "1") != "0"):
+            # shards -> pinned ring -> HBM: decode of shard i+1 overlaps the copy and the IVF assignment of shard i
+            from .ingest import add_store_pipelined
+            add_store_pipelined(index, feature_store)
+        else:
+            # the reference adds 512 rows per call (iter_batch default); larger batches amortise the call overhead
+            batches = (feature_store.iter_batch(batch_size=65536, exact=False) if isinstance(feature_store, WebdatasetStore)
+                       else feature_store.iter_batch(batch_size=65536))
+            for ids_batch, vectors_batch in batches:
+                index.add_with_ids(np.ascontiguousarray(vectors_batch, np.float32), np.ascontiguousarray(ids_batch, np.int64))
         faiss.write_index(index, index_fn.as_posix())
         self._say(f"  saved index to {index_fn}")
 

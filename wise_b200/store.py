@@ -218,6 +218,20 @@ class WebdatasetStore(FeatureStore):
         rc = fast[0].wb_tar_read(fn.encode(), self.feature_dim, rows, fast[1].ptr(ids), fast[1].ptr(x), C.byref(n))
         return (ids[: n.value], x[: n.value]) if rc == 0 else None
 
+    def decode_shard_into(self, fn, ids_out, x_out):
+        """Decode one whole shard with the C++ reader straight into caller-owned buffers (pinned host memory in
+        wise_b200.ingest): ids_out int64[cap], x_out float32[cap, d].  Returns the number of rows, or None when
+        the shard needs the python reader.  The ctypes call releases the GIL."""
+        import ctypes as C
+        fast = _fast_tar()
+        rows = getattr(self, "_shard_rows", {}).get(fn)
+        if fast is None or rows is None or self.feature_dim <= 0 or rows > ids_out.shape[0]:
+            return None
+        n = C.c_int64()
+        rc = fast[0].wb_tar_read(fn.encode(), self.feature_dim, ids_out.shape[0], fast[1].ptr(ids_out), fast[1].ptr(x_out),
+                                 C.byref(n))
+        return int(n.value) if rc == 0 else None
+
     def _fast_shards(self):
         """(fn, decoded) per shard, in shard order (shuffled when shard_shuffle is set); shard i+1 is decoded on a
         helper thread while the caller consumes shard i (only for the fp32 layout WISE writes; others yield None)."""
@@ -290,15 +304,13 @@ class WebdatasetStore(FeatureStore):
 
 
 class NumpySaveStore(FeatureStore):
+    """READ side of /root/reference/src/feature/store/numpy_save_store.py (SURVEY.md section 2 row 5 scopes this store
+    as a loader input only): shards `<name>-%06d.npz` holding `feature_id int32[n]` and `features float32[n, d]`
+    (:80-87).  Writing stays with WISE's extract-features.py and the reference's own class."""
+
     def __init__(self, store_name, store_data_dir):
         self.store_name = store_name
         self.store_data_dir = Path(store_data_dir)
-
-    def enable_write(self, shard_maxcount, shard_maxsize, verbose=0):
-        self.shard_maxcount = shard_maxcount
-        self.shard_maxsize = shard_maxsize
-        self.verbose = verbose
-        self.current_shard_index = -1
 
     def enable_read(self, shard_shuffle=False, shuffle_values=False, shuffle_bufsize=10000):
         self.shard_shuffle = shard_shuffle
@@ -321,33 +333,6 @@ class NumpySaveStore(FeatureStore):
                         raise ValueError(f"unrecognized feature shape {f0.shape}")
                     self.feature_dim = f0.shape[-1]
 
-    def add(self, id, features):
-        if self.current_shard_index == -1:
-            self.feature_dim = features.shape[1]
-            self.shard_features = np.ndarray((self.shard_maxcount, self.feature_dim), dtype=np.float32)
-            self.shard_feature_id = np.ndarray((self.shard_maxcount), dtype=np.int32)
-            self.shard_feature_index = 0
-            self.current_shard_index = 0
-        if self.feature_dim != features.shape[1]:
-            raise ValueError(f"feature dimension cannot change and must be {self.feature_dim}")
-        if features.shape[0] != 1:
-            raise ValueError(f"cannot add {features.shape[0]} features, only one feature can be added at a time")
-        if self.shard_feature_index == self.shard_maxcount:
-            self.save_current_shard()
-            self.add(id, features)
-        else:
-            self.shard_features[self.shard_feature_index] = features
-            self.shard_feature_id[self.shard_feature_index] = id
-            self.shard_feature_index += 1
-
-    def save_current_shard(self):
-        shard_id = "%s-%06d" % (self.store_name, self.current_shard_index)
-        np.savez(self.store_data_dir / shard_id, feature_id=self.shard_feature_id, features=self.shard_features)
-        if self.verbose:
-            print(f"saved {self.shard_feature_index} features to shard {shard_id}")
-        self.current_shard_index += 1
-        self.shard_feature_index = 0
-
     def _shards(self):
         for fn in self.npz_filename_list:
             with np.load(fn) as payload:
@@ -367,19 +352,11 @@ class NumpySaveStore(FeatureStore):
             for s in range(0, ids.shape[0], batch_size):
                 yield ids[s:s + batch_size].astype(np.int64), np.ascontiguousarray(feats[s:s + batch_size], np.float32)
 
-    def close(self):
-        if getattr(self, "shard_feature_index", 0) != 0:
-            self.shard_feature_id = self.shard_feature_id[: self.shard_feature_index].copy()
-            self.shard_features = self.shard_features[: self.shard_feature_index].copy()
-            self.save_current_shard()
-            self.shard_feature_index = 0
+    def enable_write(self, shard_maxcount, shard_maxsize, verbose=0):
+        raise NotImplementedError("wise_b200 only reads NumpySaveStore shards; WISE's own class writes them")
 
-    def __del__(self):
-        try:
-            if getattr(self, "shard_feature_index", 0) != 0:
-                self.close()
-        except Exception:
-            pass
+    def add(self, id, features):
+        raise NotImplementedError("wise_b200 only reads NumpySaveStore shards; WISE's own class writes them")
 
 
 class FeatureStoreType(str, enum.Enum):
