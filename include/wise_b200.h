@@ -71,6 +71,8 @@ int wb_add_with_ids_dev(wb_index* h, int64_t n, const float* x_dev, const int64_
 int wb_pinned_alloc(int64_t bytes, void** out);
 int wb_pinned_free(void* p);
 int wb_add_with_ids_pinned(wb_index* h, int64_t n, const float* x_pinned, const int64_t* ids_pinned, int slot);
+int wb_ivf_add_preassigned_pinned(wb_index* h, int64_t n, const float* x_pinned, const int64_t* ids_pinned,
+                                  const int32_t* assign_pinned, int slot); /* read_index of an IwFl file: lists known */
 int wb_add_slot_wait(wb_index* h, int slot);
 int wb_sync(wb_index* h);
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "wb_pinned_alloc": (C.c_int, [C.c_int64, C.POINTER(_vp)]),
     "wb_pinned_free": (C.c_int, [_vp]),
     "wb_add_with_ids_pinned": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int]),
+    "wb_ivf_add_preassigned_pinned": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int]),
     "wb_add_slot_wait": (C.c_int, [_vp, C.c_int]),
     "wb_sync": (C.c_int, [_vp]),
     "wb_ivf_train": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, C.c_int64]),

@@ -1156,6 +1156,19 @@ extern "C" int wb_add_with_ids_pinned(wb_index* h, int64_t n, const float* x_pin
     h->add_pending[slot] = true;
     return 0;
 }
+// Same for rows whose list is already known (faiss.read_index of an IndexIVFFlat file): no coarse quantisation.
+extern "C" int wb_ivf_add_preassigned_pinned(wb_index* h, int64_t n, const float* x_pinned, const int64_t* ids_pinned,
+                                             const int32_t* assign_pinned, int slot) {
+    if (!h || !h->ivf) return fail("not an IVF index");
+    if (!assign_pinned) return fail("assign is NULL");
+    if (slot < 0 || slot >= wb_index::kAddSlots) return fail("slot %d out of range [0, %d)", slot, wb_index::kAddSlots);
+    TRY(set_dev(h));
+    if (!h->add_ev[slot]) CK(cudaEventCreateWithFlags(&h->add_ev[slot], cudaEventDisableTiming));
+    TRY(add_common(h, n, x_pinned, ids_pinned, true, assign_pinned, h->stream, false));
+    CK(cudaEventRecord(h->add_ev[slot], h->stream));
+    h->add_pending[slot] = true;
+    return 0;
+}
 extern "C" int wb_add_slot_wait(wb_index* h, int slot) {
     if (!h) return fail("NULL index");
     if (slot < 0 || slot >= wb_index::kAddSlots) return fail("slot %d out of range [0, %d)", slot, wb_index::kAddSlots);

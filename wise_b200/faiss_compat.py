@@ -139,9 +139,9 @@ class Index:
         return D, I
 
     # -- bulk access used by write_index --------------------------------------------------------
-    def _export(self, start: int, n: int, want_assign: bool = False, want_ids: bool = True):
+    def _export(self, start: int, n: int, want_assign: bool = False, want_ids: bool = True, want_x: bool = True):
         """Storage rows [start, start+n): insertion order for flat indices, list by list for a finalized IVF index."""
-        x = np.empty((n, self.d), np.float32)
+        x = np.empty((n, self.d), np.float32) if want_x else None
         ids = np.empty((n,), np.int64) if want_ids else None
         a = np.empty((n,), np.int32) if want_assign else None
         _capi.check(_capi.lib().wb_export_rows(self._h, start, n, _capi.ptr(x), _capi.ptr(ids), _capi.ptr(a)))
@@ -287,7 +287,7 @@ class IndexIVFFlat(Index):
             return
         n = self.ntotal
         for s in range(0, n, 1 << 20):
-            _, ids, _ = self._export(s, min(1 << 20, n - s))
+            _, ids, _ = self._export(s, min(1 << 20, n - s), want_x=False)
             if ids.size and (ids.min() < 0 or ids.max() >= n):
                 raise RuntimeError("direct map supported only for seqential ids")  # (sic) faiss message
         self.direct_map.type = DirectMap.Array

@@ -23,11 +23,17 @@ RING = 3  # buffers: one being decoded into, one in flight to the GPU, one spare
 class PinnedRing:
     """RING pinned (page-locked) host buffers of `rows` x (int64 id + d floats), as numpy views."""
 
-    def __init__(self, rows: int, d: int, nbuf: int = RING):
+    def __init__(self, rows: int, d: int, nbuf: int = RING, with_assign: bool = False):
         L = _capi.lib()
         self._ptrs = []
-        self.ids, self.x = [], []
+        self.ids, self.x, self.assign = [], [], []
+        self.rows, self.d, self.nbuf = max(rows, 1), d, nbuf
         for _ in range(nbuf):
+            if with_assign:
+                p_a = C.c_void_p()
+                _capi.check(L.wb_pinned_alloc(max(rows, 1) * 4, C.byref(p_a)))
+                self._ptrs.append(p_a)
+                self.assign.append(np.ctypeslib.as_array((C.c_int32 * max(rows, 1)).from_address(p_a.value)))
             p_ids, p_x = C.c_void_p(), C.c_void_p()
             _capi.check(L.wb_pinned_alloc(max(rows, 1) * 8, C.byref(p_ids)))
             self._ptrs.append(p_ids)
@@ -38,7 +44,7 @@ class PinnedRing:
 
     def close(self):
         L = _capi.lib()
-        self.ids, self.x = [], []
+        self.ids, self.x, self.assign = [], [], []
         for p in self._ptrs:
             L.wb_pinned_free(p)
         self._ptrs = []
