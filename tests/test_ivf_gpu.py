@@ -219,3 +219,39 @@ def test_ivf_write_index_without_search_is_grouped(faiss, tmp_path):
     D1, I1 = idx.search(xq, 10)
     D2, I2 = idx2.search(xq, 10)
     assert np.array_equal(I1, I2) and np.array_equal(D1, D2)
+
+
+@pytest.mark.parametrize("n,d,nlist,k,nq", [(60000, 128, 64, 100, 96), (40000, 768, 200, 10, 33), (30000, 64, 16, 1000, 20)])
+def test_ivf_batched_listmajor_matches_oracle(faiss, monkeypatch, n, d, nlist, k, nq):
+    """Batches take the list-major kernel (ivf_lm.cuh): the probe table is inverted on the device, every probed list
+    is streamed once per group of 8 queries, thresholds are shared across work items.  Same results as the oracle
+    and as the query-major kernel, for few and many probes, including exact duplicates in different lists."""
+    from wise_b200 import _capi
+    L = _capi.lib()
+    xb = O.clustered_unit(n, d, 3 * nlist, 60)
+    xb[n - 7] = xb[11]
+    cent = O.kmeans_init(xb, nlist)
+    assign = O.ivf_assign(xb, cent).astype(np.int32)
+    assign[n - 7] = (assign[11] + 1) % nlist  # the duplicate lives in another list
+    ids = np.arange(n, dtype=np.int64) * 2 + 3
+    idx = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, nlist, faiss.METRIC_INNER_PRODUCT)
+    idx.set_centroids(cent)
+    _capi.check(L.wb_ivf_add_preassigned(idx._h, n, _capi.ptr(xb), _capi.ptr(ids), _capi.ptr(assign)))
+    xq = np.concatenate([xb[11:12], O.clustered_unit(nq - 1, d, 3 * nlist, 61)])
+    for nprobe in (1, 8, nlist):
+        idx.nprobe = nprobe
+        monkeypatch.setenv("WB_IVF_LISTMAJOR", "1")
+        l0 = L.wb_launch_count(idx._h)
+        D, I = idx.search(xq, k)
+        assert L.wb_launch_count(idx._h) - l0 >= 6, "the list-major path launches its table-building kernels"
+        monkeypatch.setenv("WB_IVF_LISTMAJOR", "0")
+        Dq, Iq = idx.search(xq, k)
+        Dr, Ir = O.ivf_search(xb, ids, assign.astype(np.int64), cent, xq, k, nprobe)
+        O.compare_topk(D, I, Dr, Ir)
+        O.compare_topk(Dq, Iq, Dr, Ir)
+        if nprobe == nlist:
+            assert I[0, 0] == ids[11] and I[0, 1] == ids[n - 7] and D[0, 0] == D[0, 1]
+    monkeypatch.delenv("WB_IVF_LISTMAJOR")
+    idx.nprobe = nlist  # nq * nprobe >= nlist: the automatic choice is list-major
+    D, I = idx.search(xq, k)
+    O.compare_topk(D, I, Dr, Ir)

@@ -18,6 +18,7 @@
 #include "exchange.cuh"
 #include "gemm.cuh"
 #include "gemm_ss.cuh"
+#include "ivf_lm.cuh"
 #include "kmeans.cuh"
 #include "merge.cuh"
 #include "scan.cuh"
@@ -124,7 +125,7 @@ struct wb_index {
     int64_t* list_off = nullptr;  // [nlist + 1]
     bool csr_dirty = true;
     // scratch
-    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gimg2, gkeys, gstate, gmargin, eD, eI, tailcnt, ccnt, ctot;
+    DevBuf parts, qbuf, dbuf, ibuf, pD, pI, xbuf, idbuf, misc, kperm, koff, gimg, gimg2, gkeys, gstate, gmargin, eD, eI, tailcnt, ccnt, ctot, lmA, lmB, lmC, lmD, lmE, lmF, lmG;
     PinBuf pin_q, pin_o;  // pinned staging of small query / result transfers of the host API
     static constexpr int kAddSlots = 8;   // wb_add_with_ids_pinned: one event per in-flight pinned buffer
     cudaEvent_t add_ev[kAddSlots] = {};
@@ -206,7 +207,8 @@ extern "C" int wb_free(wb_index* h) {
     cudaFree(h->row_pos);
     cudaFree(h->list_off);
     for (DevBuf* b : {&h->parts, &h->qbuf, &h->dbuf, &h->ibuf, &h->pD, &h->pI, &h->xbuf, &h->idbuf, &h->misc,
-                      &h->kperm, &h->koff, &h->gimg, &h->gimg2, &h->gkeys, &h->gstate, &h->gmargin, &h->eD, &h->eI, &h->tailcnt, &h->ccnt, &h->ctot})
+                      &h->kperm, &h->koff, &h->gimg, &h->gimg2, &h->gkeys, &h->gstate, &h->gmargin, &h->eD, &h->eI, &h->tailcnt, &h->ccnt, &h->ctot, &h->lmA, &h->lmB, &h->lmC,
+                      &h->lmD, &h->lmE, &h->lmF, &h->lmG})
         b->release();
     h->pin_q.release();
     h->pin_o.release();
@@ -1195,6 +1197,90 @@ extern "C" int wb_ivf_add_preassigned(wb_index* h, int64_t n, const float* x_hos
     return add_common(h, n, x_host, ids_host, true, assign_host, h->stream);
 }
 
+// ---- K5 for batches: list-major scan (ivf_lm.cuh) ------------------------------------------------------------------
+template <int RW>
+static int launch_lm_t(const LmParams& p, int grid, size_t smem, cudaStream_t st) {
+    static thread_local bool attr_done[64] = {};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_done[dev]) {
+        CK(cudaFuncSetAttribute(ivf_listmajor_kernel<8, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        if (dev < 64) attr_done[dev] = true;
+    }
+    ivf_listmajor_kernel<8, RW><<<grid, kScanThreads, smem, st>>>(p);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Taken when the probes of the batch overlap enough for shared reads to pay (on average every list is probed at
+// least once) and the rows are physically grouped by list.  WB_IVF_LISTMAJOR=0 / 1 forces it off / on.
+static int run_ivf_listmajor(wb_index* h, int64_t nq, const float* q_ld, int k, int np, float* D, int64_t* I,
+                             cudaStream_t st, bool* done) {
+    *done = false;
+    const int mode = env_int("WB_IVF_LISTMAJOR", -1);
+    if (mode == 0 || h->slot_row != nullptr || h->n == 0) return 0;
+    const int64_t npairs = nq * (int64_t)np;
+    if (mode < 0 && (nq < 8 || npairs < h->nlist)) return 0;
+    if (npairs >= ((int64_t)1 << 31) || (double)npairs * k * 8.0 > 2e9) return 0;
+    ScanCfg c;
+    if (plan_scan(h, 8, k, false, 0, &c) != 0 || c.NQ != 8 || !c.single_copy) return 0;
+    const int64_t nlist = h->nlist;
+    const int64_t max_items = npairs / 8 + nlist + 1;
+    TRY(h->lmA.ensure((size_t)npairs * 4));              // list of every (query, probe) pair
+    TRY(h->lmB.ensure((size_t)npairs * 4));              // pairs grouped by list
+    TRY(h->lmC.ensure((size_t)(nlist + 1) * 8));         // pairs per list (CSR offsets)
+    TRY(h->lmD.ensure((size_t)(nlist + 1) * 8));         // work items per list
+    TRY(h->lmE.ensure((size_t)(nlist + 1) * 8));         // first work item of every list
+    TRY(h->lmF.ensure((size_t)max_items * 4));           // list of every work item
+    TRY(h->lmG.ensure((size_t)nq * 4 + 64));             // shared thresholds + the work counter
+    TRY(h->parts.ensure((size_t)npairs * k * sizeof(uint64_t)));
+    i64_to_i32_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(h->pI.as<int64_t>(), h->lmA.as<int32_t>(), npairs);
+    CK(cudaGetLastError());
+    TRY(device_csr(h, h->lmA.as<int32_t>(), npairs, nullptr, h->lmC.as<int64_t>(), h->lmB.as<uint32_t>(), nullptr, st, false));
+    lm_item_count_kernel<<<(unsigned)((nlist + 255) / 256), 256, 0, st>>>(h->lmC.as<int64_t>(), nlist, 8, h->lmD.as<int64_t>());
+    CK(cudaGetLastError());
+    csr_offsets_kernel<<<1, 1024, 0, st>>>(h->lmD.as<int64_t>(), nlist, h->lmE.as<int64_t>());
+    CK(cudaGetLastError());
+    lm_item_fill_kernel<<<(unsigned)((nlist + 255) / 256), 256, 0, st>>>(h->lmE.as<int64_t>(), nlist, h->lmF.as<int32_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(h->lmG.p, 0, (size_t)nq * 4 + 64, st));
+    LmParams p{};
+    p.rows = h->rows;
+    p.ld = h->ld;
+    p.queries = q_ld;
+    p.nq = (int)nq;
+    p.k = k;
+    p.P = c.P;
+    p.stages = c.stages;
+    p.nprobe = np;
+    p.nlist = nlist;
+    p.list_off = h->list_off;
+    p.row_pos = h->row_pos;
+    p.pl_off = h->lmC.as<int64_t>();
+    p.pair_src = h->lmB.as<uint32_t>();
+    p.item_off = h->lmE.as<int64_t>();
+    p.item_list = h->lmF.as<int32_t>();
+    p.gthr = h->lmG.as<uint32_t>();
+    p.counter = reinterpret_cast<unsigned int*>(h->lmG.as<unsigned char>() + (size_t)nq * 4 + 16);
+    p.parts = h->parts.as<uint64_t>();
+    const int evs = (int)(h->ev_count % wb_index::kEvRing);
+    if (h->timing) CK(cudaEventRecord(h->ev0[evs], st));
+    const int grid = (int)std::min<int64_t>(h->sm_count, max_items);
+    switch (c.RW) {
+        case 4: TRY(launch_lm_t<4>(p, grid, c.smem, st)); break;
+        case 2: TRY(launch_lm_t<2>(p, grid, c.smem, st)); break;
+        default: TRY(launch_lm_t<1>(p, grid, c.smem, st)); break;
+    }
+    if (h->timing) {
+        CK(cudaEventRecord(h->ev1[evs], st));
+        h->ev_count++;
+    }
+    h->launches += 4;
+    TRY(launch_merge_keys(h, nq, k, np, h->parts.as<uint64_t>(), h->ids, D, I, st));
+    *done = true;
+    return 0;
+}
+
 // ---- search --------------------------------------------------------------------------------
 static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld] */, int64_t k, int64_t nprobe, float* D,
                            int64_t* I, cudaStream_t st, const ExchParams* ex = nullptr, bool* exchanged = nullptr) {
@@ -1209,6 +1295,13 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
     if (h->csr_dirty) {
         if (st != h->stream) CK(cudaStreamSynchronize(st));
         TRY(ensure_csr(h));
+    }
+    // K5, batches: list-major - the probe table is inverted on the device and every probed list is streamed once per
+    // group of 8 of the queries that probe it (ivf_lm.cuh)
+    {
+        bool done = false;
+        TRY(run_ivf_listmajor(h, nq, q_ld, (int)k, np, D, I, st, &done));
+        if (done) return 0;
     }
     // K5: gather-scan of the probed lists
     ScanCfg c;

@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) ivf_listmajor_kernel(const Lm
     uint64_t* empty = full + p.stages;
     int* qcnt = reinterpret_cast<int*>(smem_lm + L.misc);
     float* thr_s = reinterpret_cast<float*>(smem_lm + L.misc) + NQ;
-    int* item_s = reinterpret_cast<int*>(thr_s + NQ);  // [0] current work item (the 16 spare bytes of the layout)
-    __shared__ uint32_t pair_s[NQ];                    // (static: 32 bytes; plan_lm leaves room for it)
+    int* item_s = reinterpret_cast<int*>(thr_s + NQ);  // [0] current work item
+    uint32_t* pair_s = reinterpret_cast<uint32_t*>(item_s + 4);  // [NQ] (query, probe) pair of each query of the item
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k = p.k, P = p.P;

@@ -80,7 +80,7 @@ __host__ __device__ inline ScanSmem scan_smem_layout(int NQ, int ld, int P, int 
     o = (o + 15) & ~(size_t)15;
     L.lists = o;   o += (size_t)NQ * P * 8;
     L.bars = o;    o += (size_t)stages * 2 * 8;
-    L.misc = o;    o += (size_t)NQ * 8 + 16;  // qcnt[NQ] (int) + thr_s[NQ] (float) + fused-tail flag and counter
+    L.misc = o;    o += (size_t)NQ * 12 + 16;  // qcnt[NQ] (int) + thr_s[NQ] (float) + 4 ints (fused tail / work item) + pair[NQ] (list-major)
     o = (o + 7) & ~(size_t)7;
     L.prefix = o;  o += nprobe > 0 ? (size_t)nprobe * 8 + (size_t)(nprobe + 1) * 4 : 0;  // pbase[np] i64 + prefix[np+1] u32
     L.total = (o + 15) & ~(size_t)15;
