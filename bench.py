@@ -449,7 +449,7 @@ def run_ours(a):
         for i in range(warmup):
             sharded.search_dev(qs[i], a.k)
         barrier()
-        l0 = L.wb_launch_count(index._h)
+        l0 = L.wb_launch_count(index._h) + (L.wb_exch_launch_count(sharded.exchange.h) if sharded.exchange else 0)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for i in range(steps):
@@ -457,7 +457,7 @@ def run_ours(a):
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1) / steps
-        launches = L.wb_launch_count(index._h) - l0 + (steps if world > 1 else 0)  # + the exchange kernel per step
+        launches = (L.wb_launch_count(index._h) + (L.wb_exch_launch_count(sharded.exchange.h) if sharded.exchange else 0)) - l0
         # per-launch scan durations OF THE TIMED REGION: event pairs recorded by the library around the
         # scan kernel(s) on the launching stream (ring of 128), read back after the region has ended
         buf = (ctypes.c_float * 128)()

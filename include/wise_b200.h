@@ -12,8 +12,8 @@
  *     memory, "_dev" variants take device pointers on the index's GPU and a cudaStream_t
  *     (passed as void*) and do not synchronise.
  *   - one index lives on one GPU (one process per GPU; rows are sharded across processes by
- *     the host layer, wise_b200/sharded.py, which merges the per-GPU top-k with
- *     wb_merge_topk_dev after an NCCL all-gather).
+ *     the host layer, wise_b200/sharded.py; the per-GPU top-k lists are exchanged and merged through
+ *     NVLink peer memory by wb_exch_search*, below - NCCL is not on the search path).
  *   - results: D float32[nq*k] sorted by score descending, ties broken by lowest insertion
  *     position; I int64[nq*k]; unfilled slots are (-FLT_MAX, -1) exactly like faiss.
  *   - there is no CPU fallback: without a CUDA device every compute call fails.
@@ -108,7 +108,8 @@ int wb_kmeans_update_dev(wb_index* h, const float* sums_dev, const int64_t* coun
 /* dist, ids = index.search(x, k)   feature_search_index.py:113, api/routes.py:1407.
  * nprobe is ignored by flat indices (index.nprobe, api/routes.py:899-902). 1 <= k <= WB_MAX_K.
  * Batches of 5+ queries take the tensor-core path, which synchronises `stream` once at the end (it has to
- * read the candidate-overflow flag); smaller batches and IVF list scans stay fully asynchronous in _dev. */
+ * read the candidate-overflow flag); smaller batches and IVF list scans stay fully asynchronous in _dev and are
+ * ONE kernel launch (the scan kernel's last CTA merges the per-CTA lists and writes D / I). */
 int wb_search(wb_index* h, int64_t nq, const float* q_host, int64_t k, int64_t nprobe,
               float* D_host, int64_t* I_host);
 int wb_search_dev(wb_index* h, int64_t nq, const float* q_dev, int64_t k, int64_t nprobe,
@@ -141,6 +142,8 @@ int wb_exch_search_dev(wb_index* h, wb_exchange* ex, int64_t nq, const float* q_
 /* *timed_out = 1 when a kernel of this exchange gave up waiting for a peer (20 s): that search's results are invalid.
  * wb_exch_search checks it itself; callers of the _dev entry points check it after synchronising their stream. */
 int wb_exch_status(wb_exchange* ex, int* timed_out);
+/* exchange_merge_kernel launches so far (0 for searches whose exchange ran inside the scan kernel). */
+int64_t wb_exch_launch_count(const wb_exchange* ex);
 int wb_exch_free(wb_exchange* ex);
 
 /* ---- row access ------------------------------------------------------------------------- */
@@ -182,7 +185,7 @@ int wb_tf32_peak(int device, int iters, int reps, double* tflops_burst_out, doub
 int wb_storage(wb_index* h, void** rows_dev, int64_t* ld);
 /* Number of this library's kernels launched on behalf of `h` since creation. */
 int64_t wb_launch_count(const wb_index* h);
-/* Tensor-core path (batches >= 9 queries): epochs of gemm_topk_kernel launched so far, and how many
+/* Tensor-core path (batches of 5+ queries on large stores): epochs of the GEMM kernels launched so far, and how many
  * batches had to be repaired by the CUDA-core scan after a candidate-list overflow. */
 int wb_gemm_stats(const wb_index* h, int64_t* epochs, int64_t* fallbacks);
 /* Device time (ms, CUDA events on the index's stream) of the scan kernel(s) of the last

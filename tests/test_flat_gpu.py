@@ -227,7 +227,7 @@ def test_large_scan_properties_2m_x_768(faiss):
         assert set(better.tolist()) <= set(I[j].tolist())
 
 
-# ---- K2: tensor-core path (batches >= 9 queries) -------------------------------------------------
+# ---- K2: tensor-core path (batches of 5+ queries; WB_GEMM_FORCE=1 lifts the store-size rule) ------------
 def _gemm_stats(idx):
     from wise_b200 import _capi
     a, b = C.c_int64(), C.c_int64()
@@ -327,3 +327,21 @@ def test_gemm_overflow_falls_back_exactly(faiss, monkeypatch):
     epochs, fallbacks = _gemm_stats(idx)
     assert epochs > 0 and fallbacks == 1
     O.compare_topk(D, I, *O.flat_search(xb, xq.astype(np.float32), k))
+
+
+def test_gemm_score_audit_repeated(faiss, monkeypatch):
+    """The audit that caught the raw-stage release race in round 1 (profiles/r01/gemm_experiments.md), kept in the
+    suite: six fresh indices, every returned score of the tensor-core path recomputed in fp64, no true member missing.
+    A corrupted tile shows up as a handful of wrong entries in one 128-row tile."""
+    monkeypatch.setenv("WB_GEMM_FORCE", "1")
+    n, d, nq, k = 40000, 768, 300, 100  # 300 queries: 128-query TS blocks in epoch 0, 256-query SS blocks afterwards
+    xb = O.unit_gaussian(n, d, 100)
+    xq = O.unit_gaussian(nq, d, 200)
+    Dr, Ir = O.flat_search(xb, xq, k)
+    for trial in range(6):
+        idx = faiss.IndexFlatIP(d)
+        idx.add(xb)
+        D, I = idx.search(xq, k)
+        true = np.einsum('qkd,qd->qk', xb[I].astype(np.float64), xq.astype(np.float64))
+        assert np.abs(true - D).max() <= 1e-5, (trial, float(np.abs(true - D).max()))
+        O.compare_topk(D, I, Dr, Ir, band=4e-6)

@@ -58,6 +58,7 @@ SIGNATURES = {
     "wb_exch_merge_dev": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "wb_exch_search": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, _vp]),
     "wb_exch_search_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp]),
+    "wb_exch_launch_count": (C.c_int64, [_vp]),
     "wb_exch_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "wb_exch_free": (C.c_int, [_vp]),
     "wb_reconstruct_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp]),

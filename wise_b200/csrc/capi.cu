@@ -936,7 +936,7 @@ static int run_flat_any(wb_index* h, const float* rows, int64_t nrows, const flo
         h->gemm_fallbacks++;
     }
     return run_flat_scan(h, rows, nrows, q_dev, nq, k, ids, D, I, st, timed,
-                         ex && nq <= kMaxGridY ? ex : nullptr, exchanged);
+                         ex && nq <= kMaxGridY && env_int("WB_FUSE_EXCH", 1) ? ex : nullptr, exchanged);
 }
 
 // ---- K8: CSR inverted lists, built on the device (csr.cuh) -------------------------------------------------------
@@ -1318,7 +1318,7 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
     p.row_pos = h->row_pos;
     p.list_off = h->list_off;
     p.nprobe = np;
-    if (ex && nq > kMaxGridY) ex = nullptr;
+    if (ex && (nq > kMaxGridY || !env_int("WB_FUSE_EXCH", 1))) ex = nullptr;
     int S_merge = 0;
     const bool fuse = tail_fusable(c, (int)k, S, ex ? ex->world : 1, &S_merge);
     if (fuse) {
@@ -1855,6 +1855,7 @@ struct wb_exchange {
     bool opened[kExchMaxWorld] = {};
     uint32_t seq = 0;       // sequence number of the last exchange that was LAUNCHED (all ranks advance in lockstep)
     int* status = nullptr;  // device word raised by a kernel whose wait for the peers timed out
+    int64_t launches = 0;   // exchange_merge_kernel launches (the fused path needs none)
 };
 
 extern "C" int wb_exch_create(int device, int rank, int world, int64_t max_queries, int64_t max_entries,
@@ -1963,6 +1964,7 @@ static int launch_exchange_kernel(wb_exchange* ex, ExchParams& p, const float* D
     exchange_merge_kernel<<<(unsigned)p.nq, kMergeThreads, (size_t)p.S * 8, st>>>(p);
     CK(cudaGetLastError());
     exch_commit(ex, p);
+    ex->launches++;
     return 0;
 }
 
@@ -1978,6 +1980,8 @@ extern "C" int wb_exch_merge_dev(wb_exchange* ex, int64_t nq, int64_t k, const f
 
 // 1 when a kernel of this exchange gave up waiting for a peer (a rank that never launched): the results of that
 // search are invalid.  Reads the device word (synchronises with the kernels that wrote it only if the caller did).
+extern "C" int64_t wb_exch_launch_count(const wb_exchange* ex) { return ex ? ex->launches : -1; }
+
 extern "C" int wb_exch_status(wb_exchange* ex, int* timed_out) {
     if (!ex || !timed_out) return fail("NULL argument");
     CK(cudaSetDevice(ex->device));

@@ -1,9 +1,10 @@
-// kmeans.cuh - K7 kmeans_update: deterministic per-list sums, mean, spherical renormalisation.
+// kmeans.cuh - K7 kmeans_update: deterministic per-list sums, mean, optional spherical renormalisation.
 // Replaces faiss Clustering::train's compute_centroids + post_process_centroids
 // [faiss-upstream], reached from index.train(), /root/reference/src/index/feature_search_index.py:75.
-// (K6, the assignment, is scan_topk_kernel with k = 1 over the centroids.)
-// HBM-bound: n*d*4 bytes read once, nlist*d*4 written.  No float atomics: each list is summed
-// by one CTA in insertion order, so training is bit-reproducible.
+// (K6, the assignment, runs on the tensor cores: filter2_topk_kernel<ARGMAX> for training iterations,
+// gemm2_topk_kernel<128, ARGMAX> (3xTF32) for add-time assignment; the grouping of the points by centroid is
+// csr.cuh.)  HBM-bound: n*d*4 bytes read once, nlist*d*4 written.  No float atomics: each list is summed in
+// insertion order with a fixed interleave, so training is bit-reproducible.
 #pragma once
 #include "common.cuh"
 
