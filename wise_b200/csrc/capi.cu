@@ -557,6 +557,14 @@ static int get_tensormap_encoder(PFN_encodeTiled* out) {
     return 0;
 }
 
+// Cost model behind the K1 / K2 choice, measured on B200 (profiles/r01/small_store_latency.txt, batch sweeps of
+// profiles/r01 and r02): an 8-query K1 pass streams the rows at ~4.2 TB/s-equivalent (FMA-bound at 8 queries per CTA);
+// K2 streams them once at ~6 TB/s but pays ~0.3 ms per search for its epoch launches, compactions and the one
+// stream synchronisation that reads the overflow flag.
+constexpr double kK1BatchBytesPerS = 4.2e12;
+constexpr double kK2StreamBytesPerS = 6.0e12;
+constexpr double kK2FixedSeconds = 0.3e-3;
+
 // Can the tensor-core path take this problem?  (candidate capacity `cap` rows form epoch 0)
 static bool gemm_eligible(const wb_index* h, int64_t nrows, int64_t nq, int k, int* cap_out) {
     if (env_int("WB_GEMM", 1) == 0) return false;
@@ -570,7 +578,7 @@ static bool gemm_eligible(const wb_index* h, int64_t nrows, int64_t nq, int k, i
     if (env_int("WB_GEMM_FORCE", 0) == 0) {
         const double bytes = (double)nrows * h->ld * 4.0;
         const double passes = (double)((nq + 7) / 8);
-        if (passes * bytes / 4.2e12 < 0.3e-3 + bytes / 6.0e12) return false;
+        if (passes * bytes / kK1BatchBytesPerS < kK2FixedSeconds + bytes / kK2StreamBytesPerS) return false;
     }
     *cap_out = (int)cap;
     return true;

@@ -10,12 +10,43 @@
 
 namespace wb {
 
-// sums[c, 0:d] = sum over slots of list c of x[perm[slot], 0:d]; counts[c] = list size
+// sums[c, 0:d] = sum over slots of list c of x[perm[slot], 0:d]; counts[c] = list size.
+// One CTA per list; a thread owns 4 adjacent columns (one 128-bit load per row) when d and ldx allow it, rows are
+// taken four at a time into four accumulators per column that are combined as (a0 + a1) + (a2 + a3): the order is
+// static, so the sums do not depend on the schedule.
 __global__ void __launch_bounds__(256) segment_sum_kernel(const float* x, int ldx, int d, const uint32_t* perm,
                                                           const int64_t* off, float* sums, int64_t* counts) {
     const int64_t c = blockIdx.x;
     const int64_t b = off[c], e = off[c + 1];
     if (threadIdx.x == 0) counts[c] = e - b;
+    if (((d | ldx) & 3) == 0) {
+        const int d4 = d >> 2, ld4 = ldx >> 2;
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        for (int col = threadIdx.x; col < d4; col += blockDim.x) {
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+            int64_t s = b;
+            for (; s + 4 <= e; s += 4) {
+                const uint32_t r0 = perm[s], r1 = perm[s + 1], r2 = perm[s + 2], r3 = perm[s + 3];
+                const float4 v0 = __ldg(x4 + (size_t)r0 * ld4 + col), v1 = __ldg(x4 + (size_t)r1 * ld4 + col);
+                const float4 v2 = __ldg(x4 + (size_t)r2 * ld4 + col), v3 = __ldg(x4 + (size_t)r3 * ld4 + col);
+                a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+                a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+                a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+                a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+            }
+            for (; s < e; ++s) {
+                const float4 v = __ldg(x4 + (size_t)perm[s] * ld4 + col);
+                a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w;
+            }
+            float4 r;
+            r.x = (a0.x + a1.x) + (a2.x + a3.x);
+            r.y = (a0.y + a1.y) + (a2.y + a3.y);
+            r.z = (a0.z + a1.z) + (a2.z + a3.z);
+            r.w = (a0.w + a1.w) + (a2.w + a3.w);
+            reinterpret_cast<float4*>(sums + c * d)[col] = r;
+        }
+        return;
+    }
     for (int col = threadIdx.x; col < d; col += blockDim.x) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // fixed 4-way interleave: order is static
         int64_t s = b;
