@@ -344,7 +344,7 @@ static int plan_scan(const wb_index* h, int64_t nq, int k, bool gather, int npro
                 const size_t stage_bytes = (size_t)gr * ld * 4;
                 if (fixed + 2 * stage_bytes + 64 > (size_t)h->smem_max) continue;
                 if (stage_bytes >= (1u << 20)) continue;  // mbarrier tx-count limit
-                const int stages = (int)std::min<size_t>(max_stages, ((size_t)h->smem_max - fixed - 64) / (stage_bytes + 16));
+                const int stages = (int)std::min<size_t>(max_stages, ((size_t)h->smem_max - fixed - 64) / (stage_bytes + 24));
                 *c = ScanCfg{NQ, RW, P, ld, 1, stages, gather ? 0 : 1, 0};
                 c->smem = scan_smem_layout(NQ, ld, P, ld, stages, np, gr).total;
                 return 0;
@@ -356,7 +356,7 @@ static int plan_scan(const wb_index* h, int64_t nq, int k, bool gather, int npro
             const size_t fixed = scan_smem_layout(NQ, ld, P, ck, 0, np, gr).total;
             const size_t stage_bytes = (size_t)gr * ck * 4;
             if (fixed + 2 * stage_bytes + 64 > (size_t)h->smem_max) continue;
-            const int stages = (int)std::min<size_t>(max_stages, ((size_t)h->smem_max - fixed - 64) / (stage_bytes + 16));
+            const int stages = (int)std::min<size_t>(max_stages, ((size_t)h->smem_max - fixed - 64) / (stage_bytes + 24));
             *c = ScanCfg{NQ, RW, P, ck, (ld + ck - 1) / ck, stages, 0, 0};
             c->smem = scan_smem_layout(NQ, ld, P, ck, stages, np, gr).total;
             return 0;
@@ -449,8 +449,8 @@ static int launch_merge_keys(wb_index* h, int64_t nq, int k, int64_t nparts, con
 constexpr int64_t kMaxGridY = 32768;
 static int ensure_tail_counters(wb_index* h, cudaStream_t st) {
     if (h->tailcnt.p) return 0;
-    TRY(h->tailcnt.ensure((size_t)kMaxGridY * sizeof(unsigned int)));
-    CK(cudaMemsetAsync(h->tailcnt.p, 0, (size_t)kMaxGridY * sizeof(unsigned int), st));
+    TRY(h->tailcnt.ensure((size_t)2 * kMaxGridY * sizeof(unsigned int)));  // [arrivals | row-group dispensers]
+    CK(cudaMemsetAsync(h->tailcnt.p, 0, (size_t)2 * kMaxGridY * sizeof(unsigned int), st));
     return 0;
 }
 
@@ -466,11 +466,12 @@ static bool tail_fusable(const ScanCfg& c, int k, int64_t nparts, int world, int
     return true;
 }
 
-static void set_tail(ScanParams& p, wb_index* h, int S_merge, const int64_t* ids, float* D, int64_t* I, int k,
-                     const ExchParams* ex) {
+static void set_tail(ScanParams& p, wb_index* h, const ScanCfg& c, int S_merge, const int64_t* ids, float* D, int64_t* I,
+                     int k, const ExchParams* ex) {
     p.fuse_tail = 1;
     p.S_merge = S_merge;
     p.tail_count = h->tailcnt.as<unsigned int>();
+    p.group_count = (c.nchunks == 1 && env_int("WB_SCAN_DYNAMIC", 1)) ? h->tailcnt.as<unsigned int>() + kMaxGridY : nullptr;
     p.ids = ids;
     p.D = D;
     p.I = I;
@@ -510,7 +511,7 @@ static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const fl
     const bool fuse = tail_fusable(c, k, S, ex ? ex->world : 1, &S_merge);
     if (fuse) {
         TRY(ensure_tail_counters(h, st));
-        set_tail(p, h, S_merge, ids, ex ? ex->D : D, ex ? ex->I : I, k, ex);
+        set_tail(p, h, c, S_merge, ids, ex ? ex->D : D, ex ? ex->I : I, k, ex);
     }
     const int evs = (int)(h->ev_count % wb_index::kEvRing);
     if (timed && h->timing) CK(cudaEventRecord(h->ev0[evs], st));
@@ -1331,7 +1332,7 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
     const bool fuse = tail_fusable(c, (int)k, S, ex ? ex->world : 1, &S_merge);
     if (fuse) {
         TRY(ensure_tail_counters(h, st));
-        set_tail(p, h, S_merge, h->ids, ex ? ex->D : D, ex ? ex->I : I, (int)k, ex);
+        set_tail(p, h, c, S_merge, h->ids, ex ? ex->D : D, ex ? ex->I : I, (int)k, ex);
     }
     const int evs = (int)(h->ev_count % wb_index::kEvRing);
     if (h->timing) CK(cudaEventRecord(h->ev0[evs], st));

@@ -60,6 +60,11 @@ struct ScanParams {
     int fuse_tail;
     int S_merge;              // sort-buffer entries of the fused merge (the idle ring holds them)
     unsigned int* tail_count; // [gridDim.y] arrival counters, zero between launches (the last CTA resets its own)
+    // dynamic row-group scheduling (fused-tail launches with whole-row stages): CTAs draw the next row group from
+    // group_count[blockIdx.y] instead of striding by gridDim.x.  SMs stream at slightly different rates (ncu: the
+    // fastest SM of a statically partitioned scan idles for 6-10 % of the kernel); with a shared dispenser every SM
+    // works until the rows run out.  The result does not depend on who scans what: keys carry positions.
+    unsigned int* group_count; // [gridDim.y], zero between launches (reset with tail_count); null: static partition
     const int64_t* ids;       // position -> external id (null: id = position)
     float* D;                 // [nq][k]
     int64_t* I;
@@ -79,7 +84,7 @@ __host__ __device__ inline ScanSmem scan_smem_layout(int NQ, int ld, int P, int 
     L.queries = o; o += (size_t)NQ * ld * 4;
     o = (o + 15) & ~(size_t)15;
     L.lists = o;   o += (size_t)NQ * P * 8;
-    L.bars = o;    o += (size_t)stages * 2 * 8;
+    L.bars = o;    o += (size_t)stages * 2 * 8 + (size_t)stages * 8;  // full[], empty[], group id of each stage
     L.misc = o;    o += (size_t)NQ * 12 + 16;  // qcnt[NQ] (int) + thr_s[NQ] (float) + 4 ints (fused tail / work item) + pair[NQ] (list-major)
     o = (o + 7) & ~(size_t)7;
     L.prefix = o;  o += nprobe > 0 ? (size_t)nprobe * 8 + (size_t)(nprobe + 1) * 4 : 0;  // pbase[np] i64 + prefix[np+1] u32
@@ -144,6 +149,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.lists);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint64_t* empty = full + p.stages;
+    long long* stage_group = reinterpret_cast<long long*>(empty + p.stages);  // dynamic mode: row group in each stage
     int* qcnt = reinterpret_cast<int*>(smem + L.misc);
     float* thr_s = reinterpret_cast<float*>(smem + L.misc) + NQ;
     int64_t* pbase = reinterpret_cast<int64_t*>(smem + L.prefix);
@@ -223,19 +229,34 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             if (lane >= kGroupRows || pos >= total) return 0;
             return GATHER ? (int64_t)gather_row(G, (uint32_t)pos) : pos;
         };
-        int64_t row_next = blockIdx.x < ngroups ? lookup(blockIdx.x) : 0;
-        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const bool dyn = p.group_count != nullptr;
+        // next row group of this CTA: the shared dispenser (dynamic) or the static stride
+        auto draw = [&](int64_t cur) -> int64_t {
+            if (!dyn) return cur + gridDim.x;
+            unsigned int v = 0;
+            if (lane == 0) v = atomicAdd(&p.group_count[blockIdx.y], 1u);
+            return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+        };
+        int64_t g = dyn ? draw(0) : (int64_t)blockIdx.x;
+        int64_t row_next = g < ngroups ? lookup(g) : 0;
+        for (; g < ngroups;) {
             const int64_t p0 = g * kGroupRows;
             const int nvalid = (int)min((int64_t)kGroupRows, total - p0);
             int64_t row = row_next;
-            if (p.prefetch_idx) {
-                if (g + gridDim.x < ngroups) row_next = lookup(g + gridDim.x);
+            // the next group is drawn (and its row indices looked up) now, one iteration ahead: the atomic and the
+            // CSR loads are in flight while this group's copies are issued
+            const int64_t g_next = draw(g);
+            if (p.prefetch_idx || dyn) {
+                if (g_next < ngroups) row_next = lookup(g_next);
             } else if (g != (int64_t)blockIdx.x) {
                 row = lookup(g);
             }
             const float* src = p.rows + (size_t)row * ld;
             for (int ch = 0; ch < p.nchunks; ++ch) {
-                if (lane == 0) mbar_wait(&empty[s], ph ^ 1u);
+                if (lane == 0) {
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    if (dyn) stage_group[s] = g;  // published to the consumers by the arrive below
+                }
                 __syncwarp();
                 const int cfl = min(ck, ld - ch * ck);
                 const uint32_t cbytes = (uint32_t)cfl * 4u;
@@ -260,6 +281,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                 }
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
+            g = g_next;
+        }
+        if (dyn && lane == 0) {  // end marker: the consumers learn that the dispenser is empty
+            mbar_wait(&empty[s], ph ^ 1u);
+            stage_group[s] = -1;
+            mbar_arrive(&full[s]);
         }
     } else {
         // ================================ consumers =========================================
@@ -270,12 +297,18 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         const float4* q4 = reinterpret_cast<const float4*>(qs);
         int s = 0;
         uint32_t ph = 0;
-        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const bool dyn = p.group_count != nullptr;
+        for (int64_t g = blockIdx.x; dyn || g < ngroups; g += gridDim.x) {
             float acc[V];
 #pragma unroll
             for (int i = 0; i < V; ++i) acc[i] = 0.f;
-            for (int ch = 0; ch < p.nchunks; ++ch) {
+            if (dyn) {  // (whole-row stages only: one stage per group)
                 mbar_wait(&full[s], ph);
+                g = stage_group[s];
+                if (g < 0) break;
+            }
+            for (int ch = 0; ch < p.nchunks; ++ch) {
+                if (!dyn) mbar_wait(&full[s], ph);
                 const float4* tile =
                     reinterpret_cast<const float4*>(ring + (size_t)s * stage_floats) + (size_t)(cw * kRowsPerWarp) * ck4;
                 const int c4n = min(ck4, d4 - ch * ck4);
@@ -352,7 +385,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         if (ctid == 0) {
             const unsigned int prev = atomicAdd(&p.tail_count[blockIdx.y], 1u);
             tail_last = prev == gridDim.x - 1;
-            if (tail_last) p.tail_count[blockIdx.y] = 0;  // ready for the next launch on this stream
+            if (tail_last) {  // ready for the next launch on this stream (every CTA has drawn its last group by now)
+                p.tail_count[blockIdx.y] = 0;
+                if (p.group_count) p.group_count[blockIdx.y] = 0;
+            }
         }
         named_bar_sync(kBarConsumers, kConsumerThreads);
         if (!tail_last) return;
