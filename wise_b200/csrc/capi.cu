@@ -609,7 +609,7 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     const int nq_pad = use_f2 ? nqb2 * kF2BN : nqb * kGemmBN;  // thresholds / margins of padding queries: +inf / 0
     TRY(h->gimg.ensure((size_t)nqb * nchunks * kGemmBBytes));
     TRY(h->gkeys.ensure((size_t)nq * kstride * sizeof(uint64_t)));
-    TRY(h->gstate.ensure((size_t)nq_pad * 4 + (size_t)nq * 4 + 64));
+    TRY(h->gstate.ensure((size_t)nq_pad * 4 + (size_t)nq * 4 + 64 + 64 * 4));  // thr | cnt | overflow | one work dispenser per epoch
     float* thr = h->gstate.as<float>();
     float* margin = nullptr;
     if (filter) {
@@ -633,6 +633,10 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     }
     int* cnt = reinterpret_cast<int*>(thr + (size_t)nq_pad);
     int* overflow = cnt + nq;
+    unsigned int* dispensers = reinterpret_cast<unsigned int*>(overflow + 16);  // [64], zeroed once per search
+    const bool dyn_work = env_int("WB_GEMM_DYNAMIC", 1) != 0;
+    if (dyn_work) CK(cudaMemsetAsync(dispensers, 0, 64 * sizeof(unsigned int), st));
+    int epoch_no = 0;
     uint64_t* keys = h->gkeys.as<uint64_t>();
     {
         const int64_t n1 = std::max<int64_t>((int64_t)nq_pad, nq * (int64_t)k);
@@ -763,6 +767,8 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
             }
         }
         if (!use2 && !launched) {
+            // SMs stream at different rates: (tile, block) items are drawn from a dispenser, not dealt out statically
+            g.work_counter = dyn_work && epoch_no < 64 ? dispensers + epoch_no : nullptr;
             if (one_term) gemm_topk_kernel<BN, false, 1><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
             else gemm_topk_kernel<BN, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
         }
@@ -780,6 +786,7 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
         CK(cudaGetLastError());
         h->launches += 2;
         h->gemm_launches++;
+        epoch_no++;
         r0 = r1;
     }
     if (timed && h->timing) {

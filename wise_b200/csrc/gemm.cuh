@@ -44,6 +44,11 @@ constexpr int kGemmThreads = 512;
 constexpr int kGemmABytes = kGemmBM * kGemmBK * 4;       // 16 KB raw row tile
 constexpr int kTmemCols = 512;
 constexpr int kBarEpilogue = 2;
+// Dynamic work distribution (search mode of the 1-CTA kernel): producer A draws (row tile, query block) items from a
+// global dispenser and hands them to the other roles through a small shared-memory queue.  The kernel is HBM-bound at
+// small batches and SMs stream at different rates: with the static interleave the fastest SM idled for a quarter of the
+// kernel (ncu, batch 16: SMs active 87 % on average, 75 % minimum).
+constexpr int kGemmWQ = 8;
 
 // Per query-block width BN (UMMA N = 16 / 32 / 64 / 128): small batches use a narrow block so the kernel
 // stays bound by the HBM stream of the rows instead of by padded MMAs and query-image traffic.
@@ -79,9 +84,9 @@ struct GemmCfg {
     // Ring 1: raw fp32 row tiles straight from TMA; freed by the transform warps, so it can run far ahead of
     // the MMAs - it is what keeps enough bytes in flight to cover the loaded HBM latency (~3.5 us).
     static constexpr int kRawStages = (224 * 1024 - kSlots * kBBytes) / kGemmABytes;
-    static constexpr int kNumBars = 2 * kRawStages + 2 * kSlots + 4;
+    static constexpr int kNumBars = 2 * kRawStages + 2 * kSlots + 4 + 2 * kGemmWQ;
     static constexpr size_t kSmemBytes =
-        1024 + (size_t)kRawStages * kGemmABytes + (size_t)kSlots * kBBytes + kNumBars * 8 + 16 + 2 * BN * 4;
+        1024 + (size_t)kRawStages * kGemmABytes + (size_t)kSlots * kBBytes + kNumBars * 8 + 16 + 2 * BN * 4 + kGemmWQ * 8;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
@@ -101,6 +106,7 @@ struct GemmParams {
     int* cnt;                     // [nq] candidates appended so far
     int* overflow;                // set when a candidate list ran out of room
     int k, cap, kstride;
+    unsigned int* work_counter;   // dynamic work dispenser of this launch (zero at launch); null: static interleave
 };
 
 // ---- tcgen05 / TMA PTX -----------------------------------------------------------------------
@@ -251,12 +257,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
     uint64_t* slot_empty = a_full + kSlots;
     uint64_t* d_full = slot_empty + kSlots;
     uint64_t* d_empty = d_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+    uint64_t* wq_full = d_empty + 2;          // work queue: item published by producer A
+    uint64_t* wq_empty = wq_full + kGemmWQ;   // ... and retired by the 4 epilogue warps (the last role to touch it)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wq_empty + kGemmWQ);
     float* thr_s = reinterpret_cast<float*>(tmem_slot + 2);  // [2][BN]
+    long long* wq = reinterpret_cast<long long*>(thr_s + 2 * BN);  // [kGemmWQ] work ids (-1: no more work)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ntiles = (p.row_end - p.row_begin + kGemmBM - 1) / kGemmBM;
     const int64_t nwork = ntiles * p.nqb;
+    const bool dyn = !ARGMAX && p.work_counter != nullptr;
     // Work items (row tile, query block) of this CTA.  Search mode interleaves (tile, block) pairs over the CTAs
     // (neighbouring CTAs share a row tile in L2); ARGMAX mode gives a CTA whole tiles and walks all query blocks
     // of a tile back to back, so the per-row running maximum lives in the epilogue threads' registers.
@@ -274,6 +284,28 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             qb = (int)(w - tile * p.nqb);
         }
     };
+    // Per-role cursor over the work items.  Static mode: the role's own counter.  Dynamic mode: the queue producer A
+    // fills; `last` is the queue slot of the item just taken (the epilogue retires it).
+    struct WorkCursor {
+        int slot = 0, last = 0;
+        uint32_t ph = 0;
+        int64_t it = 0;
+    };
+    auto next_item = [&](WorkCursor& c, int64_t& tile, int& qb) -> bool {
+        if (!dyn) {
+            if (c.it >= my_work) return false;
+            work_at(c.it++, tile, qb);
+            return true;
+        }
+        mbar_wait(&wq_full[c.slot], c.ph);
+        const long long w = *reinterpret_cast<volatile long long*>(&wq[c.slot]);
+        c.last = c.slot;
+        if (++c.slot == kGemmWQ) { c.slot = 0; c.ph ^= 1u; }
+        if (w < 0) return false;
+        tile = w / p.nqb;
+        qb = (int)(w - tile * p.nqb);
+        return true;
+    };
 
     if (tid == 0) {
         for (int s = 0; s < kRaw; ++s) {
@@ -287,6 +319,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(&d_full[b], 1);
             mbar_init(&d_empty[b], 4);  // 4 epilogue warps
+        }
+        for (int i = 0; i < kGemmWQ; ++i) {
+            mbar_init(&wq_full[i], 1);
+            mbar_init(&wq_empty[i], 4);
         }
         fence_mbar_init();
     }
@@ -306,10 +342,32 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         {   // the whole warp runs the control flow (converged); one elected lane issues
             int s = 0;
             uint32_t ph = 0;
-            for (int64_t it = 0; it < my_work; ++it) {
+            auto draw = [&]() -> int64_t {  // next item from the global dispenser
+                unsigned int v = 0;
+                if (lane == 0) v = atomicAdd(p.work_counter, 1u);
+                return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+            };
+            int wslot = 0;
+            uint32_t wph = 0;
+            int64_t w = dyn ? draw() : 0;
+            for (int64_t it = 0; dyn || it < my_work; ++it) {
                 int64_t tile;
                 int qb;
-                work_at(it, tile, qb);
+                if (dyn) {  // publish the item (or the end marker) to the other roles
+                    mbar_wait(&wq_empty[wslot], wph ^ 1u);
+                    if (elect_one_sync()) {
+                        wq[wslot] = w < nwork ? (long long)w : -1ll;
+                        mbar_arrive(&wq_full[wslot]);
+                    }
+                    __syncwarp();
+                    if (++wslot == kGemmWQ) { wslot = 0; wph ^= 1u; }
+                    if (w >= nwork) break;
+                    tile = w / p.nqb;
+                    qb = (int)(w - tile * p.nqb);
+                    w = draw();  // one item ahead: the atomic is in flight while this item's loads are issued
+                } else {
+                    work_at(it, tile, qb);
+                }
                 const int row0 = (int)(p.row_begin + tile * kGemmBM);
                 for (int c = 0; c < p.nchunks; ++c) {
                     mbar_wait(&raw_empty[s], ph ^ 1u);
@@ -327,10 +385,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         {
             int s = 0;
             uint32_t ph = 0;
-            for (int64_t it = 0; it < my_work; ++it) {
-                int64_t tile;
-                int qb;
-                work_at(it, tile, qb);
+            WorkCursor wc;
+            int64_t tile;
+            int qb;
+            while (next_item(wc, tile, qb)) {
                 const float* bsrc = p.bimg + (size_t)qb * p.nchunks * (kBBytes / 4);
                 for (int c = 0; c < p.nchunks; ++c) {
                     mbar_wait(&slot_empty[s], ph ^ 1u);
@@ -355,7 +413,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             uint32_t ph = 0;
             int buf = 0;
             uint32_t dph = 0;
-            for (int64_t it = 0; it < my_work; ++it) {
+            WorkCursor wc;
+            int64_t tile_;
+            int qb_;
+            while (next_item(wc, tile_, qb_)) {
                 mbar_wait(&d_empty[buf], dph ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kDCols);
@@ -410,7 +471,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             if (++ss == kSlots) { ss = 0; phs ^= 1u; }
             par ^= 1;
         };
-        for (int64_t it = 0; it < my_work; ++it) {
+        WorkCursor wc;
+        int64_t tile_;
+        int qb_;
+        while (next_item(wc, tile_, qb_)) {
             for (int c = 0; c < p.nchunks; ++c, next_chunk()) {
                 if (par != set) continue;
                 mbar_wait(&raw_full[sr], phr);
@@ -456,10 +520,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
         uint32_t dph = 0;
         float best = -INFINITY;  // ARGMAX: running maximum of this thread's row over the query blocks
         int best_i = 0;
-        for (int64_t it = 0; it < my_work; ++it) {
-            int64_t tile;
-            int qb;
-            work_at(it, tile, qb);
+        WorkCursor wc;
+        int64_t tile;
+        int qb;
+        while (next_item(wc, tile, qb)) {
             const int64_t row = p.row_begin + tile * kGemmBM + quarter * 32 + lane;
             const bool row_ok = row < p.row_end;
             if constexpr (!ARGMAX) {
@@ -535,7 +599,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&d_empty[buf]);
+            if (lane == 0) {
+                mbar_arrive(&d_empty[buf]);
+                if (dyn) mbar_arrive(&wq_empty[wc.last]);  // the last role is done with this item: its queue slot is free
+            }
             if constexpr (!ARGMAX) named_bar_sync(kBarEpilogue, 128);  // thr_s[buf] may be rewritten two tiles later
             if (++buf == 2) { buf = 0; dph ^= 1u; }
         }
