@@ -360,9 +360,11 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------
-def parity_check(src, lo, hi, q, D, I, k, world, device):
+def parity_check(src, lo, hi, q, D, I, k, world, device, allowed=None):
     """Verify (D, I) = global top-k of queries q (all [*, .] device tensors, identical on every rank) against an fp64
-    pass over THIS rank's regenerated rows; partial counts are summed over the ranks.  Returns a dict (rank-identical)."""
+    pass over THIS rank's regenerated rows; partial counts are summed over the ranks.  Returns a dict (rank-identical).
+    allowed(s, e) -> (strict, loose) bool masks [e-s, nq] restricts the candidate set (IVF: rows of the probed lists;
+    `strict` rows MUST be considered, returned rows must at least be `loose`)."""
     import torch
     import torch.distributed as dist
     nq = q.shape[0]
@@ -374,20 +376,28 @@ def parity_check(src, lo, hi, q, D, I, k, world, device):
     found = torch.zeros(nq, dtype=torch.int64, device=device)        # returned ids located in my shard
     max_err = torch.zeros(1, dtype=torch.float64, device=device)
     rows_checked = 0
+    outsiders = 0  # returned rows that are not candidates at all (IVF: not in a probed list)
     qcols = torch.arange(nq, device=device).unsqueeze(1).expand(nq, k)
     for s, e, x in src.chunks(lo, hi):
         s64 = x.double() @ q64.T                     # [m, nq] exact scores (fp64 accumulate of the fp32 inputs)
-        above += (s64 > (kth + TIE_BAND).unsqueeze(0)).sum(dim=0)
+        beats = s64 > (kth + TIE_BAND).unsqueeze(0)
+        loose = None
+        if allowed is not None:
+            strict, loose = allowed(s, e)
+            beats &= strict
+        above += beats.sum(dim=0)
         m = (I >= s) & (I < e)
         if bool(m.any()):
             ri, qi = (I[m] - s), qcols[m]
             ex = s64[ri, qi]
+            if loose is not None:
+                outsiders += int((~loose[ri, qi]).sum())
             max_err = torch.maximum(max_err, (ex - D64[m]).abs().max().reshape(1))
             ret_above.index_add_(0, qi, (ex > kth[qi] + TIE_BAND).long())
             found.index_add_(0, qi, torch.ones_like(qi))
         rows_checked += e - s
         del s64
-    t_rows = torch.tensor([rows_checked], dtype=torch.int64, device=device)
+    t_rows = torch.tensor([rows_checked, outsiders], dtype=torch.int64, device=device)
     ident = True
     if world > 1:
         for t in (above, ret_above, found, t_rows):
@@ -399,9 +409,10 @@ def parity_check(src, lo, hi, q, D, I, k, world, device):
             dist.all_reduce(mn, op=dist.ReduceOp.MIN)
             ident = ident and bool((mx == mn).all())
     sorted_ok = bool((D[:, 1:] <= D[:, :-1]).all())
-    uniq_ok = all(int(torch.unique(I[j]).numel()) == k for j in range(min(nq, 64)))
-    violations = int((above - ret_above).clamp(min=0).sum()) + int((found != k).sum())
-    return {"rows_checked": int(t_rows.item()), "queries": nq, "max_abs_err": float(max_err.item()),
+    valid = (I >= 0).sum(dim=1)  # fewer than k only when the candidate set is smaller than k (-1 padding)
+    uniq_ok = all(int(torch.unique(I[j][I[j] >= 0]).numel()) == int(valid[j]) for j in range(min(nq, 64)))
+    violations = int((above - ret_above).clamp(min=0).sum()) + int((found != valid).sum()) + int(t_rows[1].item())
+    return {"rows_checked": int(t_rows[0].item()), "queries": nq, "max_abs_err": float(max_err.item()),
             "violations": violations, "sorted": sorted_ok, "unique_ids": uniq_ok, "ranks_identical": ident,
             "score_tol": SCORE_TOL, "tie_band": TIE_BAND,
             "ok": bool(violations == 0 and float(max_err.item()) <= SCORE_TOL and sorted_ok and uniq_ok and ident)}
