@@ -255,3 +255,33 @@ def test_ivf_batched_listmajor_matches_oracle(faiss, monkeypatch, n, d, nlist, k
     idx.nprobe = nlist  # nq * nprobe >= nlist: the automatic choice is list-major
     D, I = idx.search(xq, k)
     O.compare_topk(D, I, Dr, Ir)
+
+
+def test_kmeans_split_clusters_matches_oracle(faiss):
+    """Empty lists: the host draws the (empty, donor) pairs from the list sizes with the faiss procedure (mt19937, same
+    stream as the oracle), split_apply_kernel applies them on the device.  Several empties, one donor hit twice."""
+    import ctypes as C
+    import torch
+    from wise_b200 import _capi
+    L = _capi.lib()
+    n, d, k = 3000, 32, 24
+    x = O.clustered_unit(n, d, 6, 13)
+    c0 = O.kmeans_init(x, k)
+    for dead in (3, 9, 10, 20):
+        c0[dead] = -c0[0] * (1.0 + 0.01 * dead)  # nobody's best centroid
+    idx = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, k, faiss.METRIC_INNER_PRODUCT)
+    idx.set_centroids(c0)
+    xd = torch.from_numpy(x).cuda()
+    assign = torch.empty(n, dtype=torch.int32, device="cuda")
+    sums = torch.empty(k, d, device="cuda"); counts = torch.empty(k, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    obj = C.c_double(0)
+    _capi.check(L.wb_kmeans_assign_dev(idx._h, n, xd.data_ptr(), assign.data_ptr(), C.byref(obj), st))
+    _capi.check(L.wb_kmeans_accumulate_dev(idx._h, n, xd.data_ptr(), assign.data_ptr(), sums.data_ptr(), counts.data_ptr(), st))
+    nsplit = C.c_int64(0)
+    _capi.check(L.wb_kmeans_update_dev(idx._h, sums.data_ptr(), counts.data_ptr(), n, 1234, C.byref(nsplit), st))
+    torch.cuda.synchronize()
+    c1_ref, a_ref, _, nsplit_ref = O.kmeans_iteration(x, c0)
+    assert np.array_equal(assign.cpu().numpy(), a_ref)
+    assert nsplit.value == nsplit_ref and nsplit.value >= 4
+    assert np.abs(idx.centroids() - c1_ref).max() < 1e-5

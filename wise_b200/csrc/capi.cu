@@ -1691,8 +1691,9 @@ extern "C" int wb_kmeans_update_dev(wb_index* h, const float* sums_dev, const in
     centroid_mean_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(sums_dev, counts_dev, h->centroids, ld, d, k);
     CK(cudaGetLastError());
     h->launches++;
-    // split_clusters [faiss-upstream]: an empty list takes a perturbed copy of a list picked with
-    // probability ~ its size; eps = 1/1024.  Host logic on the (small) centroid table.
+    // split_clusters [faiss-upstream]: an empty list takes a perturbed copy of a list picked with probability ~ its
+    // size; eps = 1/1024.  The pick is a sequential draw over the list sizes (host, k counters); the copies are applied
+    // on the device (split_apply_kernel) - the centroid table never leaves HBM.
     std::vector<int64_t> cnt((size_t)k);
     CK(cudaMemcpyAsync(cnt.data(), counts_dev, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1700,39 +1701,35 @@ extern "C" int wb_kmeans_update_dev(wb_index* h, const float* sums_dev, const in
     bool any_empty = false;
     for (int64_t c = 0; c < k; ++c) any_empty |= cnt[c] == 0;
     if (any_empty && n_total > k) {
-        std::vector<float> cen((size_t)k * ld);
-        CK(cudaMemcpyAsync(cen.data(), h->centroids, (size_t)k * ld * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
         std::mt19937 mt((uint32_t)seed);
         std::vector<double> hass(cnt.begin(), cnt.end());
-        const float EPS = 1.0f / 1024.0f;
+        const double denom = (double)(n_total - k);
+        std::vector<float> prob((size_t)k);  // acceptance probability of every list, kept current
+        for (int64_t c = 0; c < k; ++c) prob[c] = (float)((hass[c] - 1.0) / denom);
+        std::vector<int32_t> pairs;
         for (int64_t ci = 0; ci < k; ++ci) {
             if (hass[ci] != 0) continue;
             int64_t cj = 0;
-            for (int64_t guard = 0;; cj = (cj + 1) % k) {
-                const float p = (float)((hass[cj] - 1.0) / (double)(n_total - k));
-                const float r = (float)mt() / (float)mt.max();
-                if (r < p) break;
+            for (int64_t guard = 0;; cj = (cj + 1 == k ? 0 : cj + 1)) {
+                // (float)mt() / (float)mt.max(): the divisor is 2^32 as a float, so the product below is the same bits
+                const float r = (float)mt() * 2.3283064365386963e-10f;
+                if (r < prob[cj]) break;
                 if (++guard > k * 1000) return fail("split_clusters did not converge");
             }
-            float* a = &cen[(size_t)ci * ld];
-            float* b = &cen[(size_t)cj * ld];
-            for (int j = 0; j < d; ++j) {
-                a[j] = b[j];
-                if (j % 2 == 0) {
-                    a[j] *= 1 + EPS;
-                    b[j] *= 1 - EPS;
-                } else {
-                    a[j] *= 1 - EPS;
-                    b[j] *= 1 + EPS;
-                }
-            }
+            pairs.push_back((int32_t)ci);
+            pairs.push_back((int32_t)cj);
             hass[ci] = (double)((int64_t)hass[cj] / 2);
             hass[cj] -= hass[ci];
+            prob[ci] = (float)((hass[ci] - 1.0) / denom);
+            prob[cj] = (float)((hass[cj] - 1.0) / denom);
             nsplit++;
         }
-        CK(cudaMemcpyAsync(h->centroids, cen.data(), (size_t)k * ld * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
+        TRY(h->misc.ensure(pairs.size() * sizeof(int32_t) + 16));
+        CK(cudaMemcpyAsync(h->misc.p, pairs.data(), pairs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        split_apply_kernel<<<(unsigned)((d + 255) / 256), 256, 0, st>>>(h->centroids, ld, d, h->misc.as<int32_t>(), (int)nsplit);
+        CK(cudaGetLastError());
+        h->launches++;
+        CK(cudaStreamSynchronize(st));  // `pairs` (host) is read by the copy above
     }
     if (h->spherical) {
         renorm_rows_kernel<<<(unsigned)k, 256, 0, st>>>(h->centroids, ld, d);

@@ -73,6 +73,24 @@ __global__ void centroid_mean_kernel(const float* sums, const int64_t* counts, f
     }
 }
 
+// split_clusters [faiss-upstream], device half: the host picks, for every empty list ci, the list cj it is split from
+// (a sequential draw over the list sizes, see wb_kmeans_update_dev); this kernel applies the pairs IN ORDER: ci becomes a
+// copy of cj, the two are pushed apart by the +-1/1024 alternating perturbation.  One thread per column walks all the
+// pairs, so a pair whose cj was itself written by an earlier pair sees the updated row without any synchronisation.
+__global__ void split_apply_kernel(float* cent, int ld, int d, const int32_t* pairs, int npairs) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    const float EPS = 1.0f / 1024.0f;
+    const float fa = (j % 2 == 0) ? 1 + EPS : 1 - EPS;
+    const float fb = (j % 2 == 0) ? 1 - EPS : 1 + EPS;
+    for (int i = 0; i < npairs; ++i) {
+        const size_t ci = (size_t)pairs[2 * i], cj = (size_t)pairs[2 * i + 1];
+        const float b = cent[cj * ld + j];
+        cent[ci * ld + j] = b * fa;
+        cent[cj * ld + j] = b * fb;
+    }
+}
+
 // spherical k-means: L2-normalise each centroid row (fvec_renorm_L2); zero rows stay zero
 __global__ void __launch_bounds__(256) renorm_rows_kernel(float* cent, int ld, int d) {
     __shared__ float red[8];

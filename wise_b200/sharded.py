@@ -228,9 +228,13 @@ def train_ivf_sharded(index, x_local: torch.Tensor, niter: int = 10, seed: int =
     sums = torch.empty((k, d), dtype=torch.float32, device=dev)
     cnts = torch.empty(k, dtype=torch.int64, device=dev)
     objs = []
+    import time
+    timing = os.environ.get("WB_KMEANS_TIMING", "0") != "0"
     for it in range(niter):
         obj = C.c_double(0)
+        t0 = time.perf_counter()
         _capi.check(L.wb_kmeans_assign_fast_dev(index._h, n_local, x_local.data_ptr(), assign.data_ptr(), C.byref(obj), st))
+        t1 = time.perf_counter()
         _capi.check(L.wb_kmeans_accumulate_dev(index._h, n_local, x_local.data_ptr(), assign.data_ptr(), sums.data_ptr(),
                                                cnts.data_ptr(), st))
         o = torch.tensor([obj.value], dtype=torch.float64, device=dev)
@@ -239,12 +243,15 @@ def train_ivf_sharded(index, x_local: torch.Tensor, niter: int = 10, seed: int =
             dist.all_reduce(cnts, group=group)
             dist.all_reduce(o, group=group)
         torch.cuda.synchronize(dev)
+        t2 = time.perf_counter()
         nsplit = C.c_int64(0)
         _capi.check(L.wb_kmeans_update_dev(index._h, sums.data_ptr(), cnts.data_ptr(), n_total, 1234, C.byref(nsplit), st))
         torch.cuda.synchronize(dev)
+        t3 = time.perf_counter()
         objs.append(float(o.item()))
-        if verbose and rank == 0:
-            print(f"  k-means iteration {it}: objective {objs[-1]:.4f}, split {nsplit.value}", flush=True)
+        if (verbose or timing) and rank == 0:
+            print(f"  k-means iteration {it}: objective {objs[-1]:.4f}, split {nsplit.value}; assign {1e3 * (t1 - t0):.1f} ms, "
+                  f"group+sums+all-reduce {1e3 * (t2 - t1):.1f} ms, update {1e3 * (t3 - t2):.1f} ms", flush=True)
     _capi.check(L.wb_ivf_mark_trained(index._h))
     index._sync_quantizer()
     return objs
