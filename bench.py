@@ -284,6 +284,37 @@ def cpu_blas(sample_rows, q, k, n_full, reps=3):
     return q.shape[0] / (t_med * scale), t_med, th
 
 
+def cpu_ivf(xs, assign, centroids, q, k, nprobe, n_full, reps=3):
+    """cpu_baseline leg of config 3 (scripts/bench_configs.py): the restated IndexIVFFlat.search
+    (oracle/cpu_flat.c orc_ivf_search: parallel over queries like faiss parallel_mode 0) on a row sample with the
+    index's own centroids and list assignment; QPS scaled to n_full rows."""
+    from oracle import cpu as OC
+    OC.set_threads(host_threads())
+    nlist = centroids.shape[0]
+    order = np.argsort(assign, kind="stable").astype(np.int64)
+    offs = np.concatenate([[0], np.cumsum(np.bincount(assign, minlength=nlist))]).astype(np.int64)
+    OC.ivf_search(xs, None, offs, order, centroids, q, k, nprobe)
+    ts = []
+    for _ in range(reps):
+        t = time.perf_counter()
+        OC.ivf_search(xs, None, offs, order, centroids, q, k, nprobe)
+        ts.append(time.perf_counter() - t)
+    t_med = float(np.median(ts))
+    return q.shape[0] / (t_med * n_full / xs.shape[0]), t_med, min(q.shape[0], host_threads())
+
+
+def cpu_kmeans_iteration(xs, centroids, n_full):
+    """cpu_baseline leg of config 4: one restated Clustering iteration (oracle.kmeans_iteration: numpy / OpenBLAS fp64
+    assignment + update) on a point sample against ALL centroids; seconds scaled to n_full points."""
+    from oracle import oracle as O
+    from threadpoolctl import threadpool_limits
+    with threadpool_limits(limits=host_threads()):
+        t = time.perf_counter()
+        O.kmeans_iteration(xs, centroids)
+        dt = time.perf_counter() - t
+    return dt * n_full / xs.shape[0], dt, host_threads()
+
+
 # ------------------------------------------------------------------------------------------------
 def gen_clustered_host(n, d, seed, threads):
     """oracle.clustered_unit's distribution, generated chunk-parallel (numpy releases the GIL in the RNG)."""

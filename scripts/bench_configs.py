@@ -6,12 +6,12 @@ evidence as bench.py: roofline, clocks, an in-run parity check at size, and the 
       parity   : fp64 pass over every rank's rows restricted to the lists the coarse quantizer must probe
                  (bench.parity_check with a candidate mask): returned scores within 1e-5, no candidate outside the
                  result beats the k-th score beyond 4e-6, identical bytes on all ranks; plus recall vs exhaustive
-      cpu      : oracle/cpu_flat.c orc_ivf_search (all host threads) on a row sample with the same centroids
+      cpu      : bench.cpu_ivf - the restated IndexIVFFlat.search in C on a row sample with the same centroids
   c4: IVF k-means training, 10M x 1024 -> nlist 16384 (rows sharded, one all-reduce of sums + counts per iteration)
       roofline : tensor - 2*n*nlist*d flop per iteration / iteration time vs the TF32 peak measured in the run
       parity   : a 100k-point sample per rank: the assigned centroid's exact score is within the TF32 band of the
                  best one; centroids of 64 lists recomputed in fp64 from their members
-      cpu      : one oracle iteration (numpy/OpenBLAS assignment + update) on a bounded sample, scaled
+      cpu      : bench.cpu_kmeans_iteration - one restated iteration (numpy/OpenBLAS) on a bounded sample, scaled
 
     python scripts/bench_configs.py --config c4 [--rows N] [--niter K]
     python -m torch.distributed.run --nproc-per-node 8 scripts/bench_configs.py --config c3
@@ -132,14 +132,10 @@ if a.config == "c4":
                           "allreduce_s_per_iter": t_ar, "allreduce_share": t_ar / (dt / a.niter) if world > 1 else 0.0},
                 clocks=clocks, parity_check=parity, objective_first=objs[0], objective_last=objs[-1], mean_best_ip=objs[-1] / n)
     if rank == 0 and not a.no_cpu_baseline:
-        from oracle import oracle as O
-        from threadpoolctl import threadpool_limits
-        ncpu, kc = 20_000, k
-        xc = x[:ncpu].cpu().numpy(); cc = cent.cpu().numpy()
-        with threadpool_limits(limits=bench.host_threads()):
-            t1 = time.time(); O.kmeans_iteration(xc, cc); tc = time.time() - t1
-        line["cpu_baseline"] = {"value": tc * n / ncpu, "unit": "s per iteration", "cores": bench.host_threads(), "kind": "port",
-                                "sample": f"{ncpu} of {n} points against all {kc} centroids, one oracle.kmeans_iteration "
+        ncpu = 20_000
+        sec, tc, th = bench.cpu_kmeans_iteration(x[:ncpu].cpu().numpy(), cent.cpu().numpy(), n)
+        line["cpu_baseline"] = {"value": sec, "unit": "s per iteration", "cores": th, "kind": "port",
+                                "sample": f"{ncpu} of {n} points against all {k} centroids, one restated Clustering iteration "
                                           f"(numpy/OpenBLAS fp64 assignment + update), {tc:.2f} s scaled x{n / ncpu:g}",
                                 "host": bench.cpu_info()}
     say(**line)
@@ -230,24 +226,14 @@ else:
                                           "coarse quantizer, the merge and the NVLink exchange"},
                         clocks=clocks, parity_check=par, recall_vs_flat=rec)
             if rank == 0 and not a.no_cpu_baseline and nprobe in (8, 128):
-                from oracle import cpu as OC
-                OC.set_threads(bench.host_threads())
-                if cpu_sample is None:  # 500k rows of rank 0, grouped by their list
+                if cpu_sample is None:  # 500k rows of rank 0 with their lists
                     m = min(500_000, hi - lo)
-                    a_s = assign[:m].cpu().numpy()
-                    order = np.argsort(a_s, kind="stable").astype(np.int64)
-                    offs = np.concatenate([[0], np.cumsum(np.bincount(a_s, minlength=nlist))]).astype(np.int64)
-                    cpu_sample = (x[:m].cpu().numpy(), offs, order, cent.cpu().numpy(), m)
-                xs_, offs, order, cc, m = cpu_sample
-                qh = q.cpu().numpy()
-                OC.ivf_search(xs_, None, offs, order, cc, qh, k, nprobe)
-                ts_ = []
-                for _ in range(3):
-                    t1 = time.perf_counter(); OC.ivf_search(xs_, None, offs, order, cc, qh, k, nprobe); ts_.append(time.perf_counter() - t1)
-                tc = float(np.median(ts_))
-                line["cpu_baseline"] = {"value": nq / (tc * n / m), "unit": "queries/s", "cores": min(nq, bench.host_threads()), "kind": "port",
+                    cpu_sample = (x[:m].cpu().numpy(), assign[:m].cpu().numpy(), cent.cpu().numpy(), m)
+                xs_, as_, cc, m = cpu_sample
+                qps_c, tc, th = bench.cpu_ivf(xs_, as_, cc, q.cpu().numpy(), k, nprobe, n)
+                line["cpu_baseline"] = {"value": qps_c, "unit": "queries/s", "cores": th, "kind": "port",
                                         "sample": f"{m} of {n} rows (same centroids and lists), median {tc * 1e3:.2f} ms scaled x{n / m:g}; "
-                                                  "oracle/cpu_flat.c orc_ivf_search: parallel over queries like faiss parallel_mode 0",
+                                                  "the restated IndexIVFFlat.search (C, AVX-512), parallel over queries like faiss parallel_mode 0",
                                         "host": bench.cpu_info()}
             say(**line)
 if world > 1:

@@ -1974,7 +1974,10 @@ static int launch_exchange_kernel(wb_exchange* ex, ExchParams& p, const float* D
         CK(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
         if (ex->device < 64) attr_done[ex->device] = true;
     }
-    exchange_merge_kernel<<<(unsigned)p.nq, kMergeThreads, (size_t)p.S * 8, st>>>(p);
+    int sms = 148;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ex->device));
+    const unsigned grid = (unsigned)std::min<int64_t>(p.nq, sms);  // one resident CTA per SM at most (1024 threads)
+    exchange_merge_kernel<<<grid, kMergeThreads, (size_t)p.S * 8, st>>>(p);
     CK(cudaGetLastError());
     exch_commit(ex, p);
     ex->launches++;

@@ -11,10 +11,10 @@
 // exch_push_wait_merge is that sequence as a device function: exchange_merge_kernel runs it on a finished local
 // (D, I), and the scan kernel's tail (scan.cuh, fused mode) runs it on the top-k it has just selected, so a sharded
 // batch-1 search is a single launch per GPU.
-// A CTA depends only on the CTA that handles the same query on the other ranks, never on another local CTA, so the
-// wait cannot deadlock on residency as long as every rank launches; the wait is bounded by a wall-clock timeout
-// that raises *status instead of trapping (a trap would poison the CUDA context of every peer).  Mailboxes are
-// double-buffered by the parity of the call sequence number.
+// A CTA depends only on the CTA that handles the same query on the other ranks, never on another local CTA, and
+// grids are capped at the resident CTA count, so the wait cannot deadlock on residency as long as every rank
+// launches; the wait is bounded by a wall-clock timeout that raises *status instead of trapping (a trap would
+// poison the CUDA context of every peer).  Mailboxes are double-buffered by the parity of the call sequence number.
 #pragma once
 #include "merge.cuh"
 
@@ -136,12 +136,16 @@ __global__ void __launch_bounds__(kMergeThreads) exchange_merge_kernel(const Exc
     extern __shared__ __align__(16) unsigned char smem_merge[];
     uint64_t* buf = reinterpret_cast<uint64_t*>(smem_merge);
     __shared__ int cnt;
-    const int64_t q = blockIdx.x;
     const int k = p.k;
-    exch_push_wait_merge<kMergeThreads>(p, q, buf, &cnt, threadIdx.x, -1, [&](int j, float& d, int64_t& id) {
-        d = p.D_local[q * k + j];
-        id = p.I_local[q * k + j];
-    });
+    // The grid is capped at the number of CTAs that are resident at once and every CTA walks its queries in the same
+    // order on every rank: CTA c only ever waits for CTA c of the peers, which is resident and on the same query or
+    // ahead - the wait never depends on the order in which the hardware dispatches CTAs.
+    for (int64_t q = blockIdx.x; q < p.nq; q += gridDim.x) {
+        exch_push_wait_merge<kMergeThreads>(p, q, buf, &cnt, threadIdx.x, -1, [&](int j, float& d, int64_t& id) {
+            d = p.D_local[q * k + j];
+            id = p.I_local[q * k + j];
+        });
+    }
 }
 
 }  // namespace wb

@@ -208,9 +208,11 @@ def train_ivf_sharded(index, x_local: torch.Tensor, niter: int = 10, seed: int =
     if n_total < k:
         raise RuntimeError(f"Number of training points ({n_total}) should be at least as large as number of clusters ({k})")
     # initial centroids: k distinct global rows from a seeded permutation (same on every rank)
-    g = torch.Generator(device="cpu")
+    # (drawn on the GPU: a CPU permutation of 10M indices costs more than a training iteration; same seed and same
+    # generator on every rank, so all ranks pick the same rows)
+    g = torch.Generator(device=dev)
     g.manual_seed(seed + 1)
-    pick = torch.randperm(n_total, generator=g)[:k]
+    pick = torch.randperm(n_total, generator=g, device=dev)[:k].cpu()
     lo = int(counts[:rank].sum().item())
     mine = (pick >= lo) & (pick < lo + n_local)
     init = torch.zeros((k, d), dtype=torch.float32, device=dev)
