@@ -654,6 +654,12 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
         if (!use2) {
             split_queries_kernel<BN, kFold><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb,
                                                                                      h->gimg.as<float>());
+            if (kFold && filter) {  // the one-term epochs read a plain image (hi half only), the first epoch the folded one
+                TRY(h->gimg2.ensure((size_t)nqb * nchunks * kGemmBBytes));
+                split_queries_kernel<BN, false><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb,
+                                                                                         h->gimg2.as<float>());
+                h->launches++;
+            }
         }
         CK(cudaGetLastError());
         h->launches += 2;
@@ -677,7 +683,7 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     if (dev >= 64 || !attr_done[dev]) {
         CK(cudaFuncSetAttribute(gemm_topk_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
         CK(cudaFuncSetAttribute(gemm_topk_kernel<BN, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)kGemmSmemBytes));
+                                (int)GemmCfg<BN, false>::kSmemBytes));
         if (dev < 64) attr_done[dev] = true;
     }
     TRY(merge_smem_optin<true>());
@@ -769,8 +775,13 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
         if (!use2 && !launched) {
             // SMs stream at different rates: (tile, block) items are drawn from a dispenser, not dealt out statically
             g.work_counter = dyn_work && epoch_no < 64 ? dispensers + epoch_no : nullptr;
-            if (one_term) gemm_topk_kernel<BN, false, 1><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
-            else gemm_topk_kernel<BN, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
+            if (one_term) {
+                GemmParams g1 = g;
+                if (kFold) g1.bimg = h->gimg2.as<float>();
+                gemm_topk_kernel<BN, false, 1><<<grid, kGemmThreads, GemmCfg<BN, false>::kSmemBytes, st>>>(tmap, g1);
+            } else {
+                gemm_topk_kernel<BN, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(tmap, g);
+            }
         }
         CK(cudaGetLastError());
         const bool last = r1 >= nrows;

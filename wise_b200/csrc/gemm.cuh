@@ -239,7 +239,8 @@ template <int BN, bool ARGMAX, int TERMS = 3>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
     static_assert(TERMS == 3 || (TERMS == 1 && !ARGMAX), "one-term scores are only a filter");
-    constexpr bool FOLD = kGemmFold<BN, ARGMAX>;
+    // one-term epochs use the plain (non-folded) image: hi and lo are apart, only the hi half is copied
+    constexpr bool FOLD = kGemmFold<BN, ARGMAX> && TERMS == 3;
     using Cfg = GemmCfg<BN, FOLD>;
     constexpr int kDCols = Cfg::kDCols;
     constexpr int kRaw = Cfg::kRawStages;
@@ -393,8 +394,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
                 for (int c = 0; c < p.nchunks; ++c) {
                     mbar_wait(&slot_empty[s], ph ^ 1u);
                     if (elect_one_sync()) {
-                        mbar_arrive_expect_tx(&a_full[s], kBBytes);
-                        bulk_g2s(bimg_s + (size_t)s * kBBytes, bsrc + (size_t)c * (kBBytes / 4), kBBytes, &a_full[s]);
+                        // (non-folded images keep hi and lo apart: one-term epochs copy the hi half only)
+                        constexpr uint32_t kCopy = (TERMS == 1 && !FOLD) ? kBBytes / 2 : kBBytes;
+                        mbar_arrive_expect_tx(&a_full[s], kCopy);
+                        bulk_g2s(bimg_s + (size_t)s * kBBytes, bsrc + (size_t)c * (kBBytes / 4), kCopy, &a_full[s]);
                     }
                     __syncwarp();
                     if (++s == kSlots) { s = 0; ph ^= 1u; }
@@ -792,8 +795,11 @@ gemm2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) 
             for (int c = 0; c < p.nchunks; ++c) {
                 mbar_wait_cluster(&b_empty[s], ph ^ 1u);
                 if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(&b_full[s], kBBytes);
-                    bulk_g2s(bimg_s + (size_t)s * kBBytes, bsrc + (size_t)c * (kBBytes / 4), kBBytes, &b_full[s]);
+                    // one-term epochs read only the hi half of the image (the first half of a chunk's image): half
+                    // the L2 -> SM bytes of the query operand, which is what bounds a single 128-query block
+                    constexpr uint32_t kCopy = TERMS == 1 ? kBBytes / 2 : kBBytes;
+                    mbar_arrive_expect_tx(&b_full[s], kCopy);
+                    bulk_g2s(bimg_s + (size_t)s * kBBytes, bsrc + (size_t)c * (kBBytes / 4), kCopy, &b_full[s]);
                 }
                 __syncwarp();
                 if (++s == kBSlots) { s = 0; ph ^= 1u; }
