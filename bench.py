@@ -559,6 +559,8 @@ def run_ours(a):
         """TF32 tensor peak of THIS GPU with the library's own MMA shape: burst (one 5 ms launch) and sustained
         (~2 s back to back, second half timed: the power cap has settled)."""
         if not tf32_peak:
+            torch.cuda.synchronize()
+            time.sleep(1.0)  # the burst figure is taken first, on a GPU that has idled: not in the wake of a capped run
             tb, ts = ctypes.c_double(), ctypes.c_double()
             _capi.check(L.wb_tf32_peak(local_rank, 20000, 400, ctypes.byref(tb), ctypes.byref(ts)))
             tf32_peak.update({"burst": tb.value, "sustained": ts.value})

@@ -1421,23 +1421,29 @@ static int stage_queries(wb_index* h, int64_t nq, const float* q, bool host, cud
 }
 
 // (D, I) device -> caller's host buffers, then ONE synchronisation of the stream.
+// `word_dev` (optional): one more device int fetched with the results (the exchange's time-out flag), so that reading
+// it costs no synchronisation of its own.
 static int fetch_results(wb_index* h, int64_t nq, int64_t k, const float* D_dev, const int64_t* I_dev, float* D_host,
-                         int64_t* I_host, cudaStream_t st) {
+                         int64_t* I_host, cudaStream_t st, const int* word_dev = nullptr, int* word_host = nullptr) {
     const size_t dbytes = (size_t)nq * k * sizeof(float), ibytes = (size_t)nq * k * sizeof(int64_t);
-    if (dbytes + ibytes <= kPinStageMax) {
-        PinBuf& pb = h->pin_o;
-        TRY(pb.ensure(dbytes + ibytes));
-        unsigned char* stage = reinterpret_cast<unsigned char*>(pb.p);
+    PinBuf& pb = h->pin_o;
+    const bool staged = dbytes + ibytes <= kPinStageMax;
+    TRY(pb.ensure((staged ? dbytes + ibytes : 0) + 16));
+    unsigned char* stage = reinterpret_cast<unsigned char*>(pb.p);
+    int* word_stage = reinterpret_cast<int*>(stage + (staged ? ((dbytes + ibytes + 7) & ~(size_t)7) : 0));
+    if (word_dev) CK(cudaMemcpyAsync(word_stage, word_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (staged) {
         CK(cudaMemcpyAsync(stage, I_dev, ibytes, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(stage + ibytes, D_dev, dbytes, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         memcpy(I_host, stage, ibytes);
         memcpy(D_host, stage + ibytes, dbytes);
-        return 0;
+    } else {
+        CK(cudaMemcpyAsync(D_host, D_dev, dbytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(I_host, I_dev, ibytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
     }
-    CK(cudaMemcpyAsync(D_host, D_dev, dbytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(I_host, I_dev, ibytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (word_dev && word_host) *word_host = *word_stage;
     return 0;
 }
 
@@ -2137,9 +2143,8 @@ extern "C" int wb_exch_search(wb_index* h, wb_exchange* ex, int64_t nq, const fl
     TRY(h->eD.ensure((size_t)nq * k * sizeof(float)));
     TRY(h->eI.ensure((size_t)nq * k * sizeof(int64_t)));
     TRY(exch_search_dev_impl(h, ex, nq, q, k, nprobe, h->eD.as<float>(), h->eI.as<int64_t>(), st));
-    TRY(fetch_results(h, nq, k, h->eD.as<float>(), h->eI.as<int64_t>(), D_host, I_host, st));
     int timed_out = 0;
-    CK(cudaMemcpy(&timed_out, ex->status, sizeof(int), cudaMemcpyDeviceToHost));
+    TRY(fetch_results(h, nq, k, h->eD.as<float>(), h->eI.as<int64_t>(), D_host, I_host, st, ex->status, &timed_out));
     if (timed_out) return fail("sharded search: a peer GPU did not join the exchange within 20 s (results invalid)");
     return 0;
 }

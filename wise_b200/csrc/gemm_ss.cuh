@@ -101,13 +101,16 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
     const int64_t ntp = (ntiles + 1) / 2;  // tile pairs
     const int64_t nwork = ntp * p.nqb;
     const int64_t my_tp = ntp > pair ? (ntp - pair + npairs - 1) / npairs : 0;
-    const int64_t my_work = ARGMAX ? my_tp * p.nqb : (nwork > pair ? (nwork - pair + npairs - 1) / npairs : 0);
-    // search: (tile pair, query block) items are interleaved over the pairs - neighbouring pairs work on the same rows
-    // with different query blocks at the same time, so only the first of them misses L2.  ARGMAX: a pair owns whole
-    // tile pairs and walks every centroid block of one before it moves on (the running maximum lives in registers).
+    // A pair owns whole tile pairs and walks all query blocks of one before it moves on: the row tile is fetched from
+    // DRAM once and re-read from L2 by the SAME pair a few microseconds later.  (Interleaving the blocks of a tile over
+    // neighbouring pairs relied on those pairs staying in step; they drift, and ncu showed 1.9x the algorithmic DRAM
+    // bytes.)  Small epochs keep the interleave, which balances better when there are few tile pairs per CTA pair.
+    // ARGMAX needs the tile-major order anyway: the running maximum lives in the epilogue's registers.
+    const bool tile_major = ARGMAX || ntp >= 8 * npairs;
+    const int64_t my_work = tile_major ? my_tp * p.nqb : (nwork > pair ? (nwork - pair + npairs - 1) / npairs : 0);
     auto work_at = [&](int64_t it, int64_t& tile, int& qb) {  // tile = THIS CTA's row tile
         int64_t tp;
-        if (ARGMAX) {
+        if (tile_major) {
             const int64_t t = it / p.nqb;
             tp = pair + t * npairs;
             qb = (int)(it - t * p.nqb);
