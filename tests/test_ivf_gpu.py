@@ -1,6 +1,8 @@
 """GPU parity tests for IndexIVFFlat (coarse quantizer, list scan, add, k-means) vs the CPU oracle.
 Search is compared on the oracle's own centroids so k-means randomness is out of the picture
 (BASELINE.json north_star)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -285,3 +287,67 @@ def test_kmeans_split_clusters_matches_oracle(faiss):
     assert np.array_equal(assign.cpu().numpy(), a_ref)
     assert nsplit.value == nsplit_ref and nsplit.value >= 4
     assert np.abs(idx.centroids() - c1_ref).max() < 1e-5
+
+
+@pytest.mark.parametrize("n,nlist,skew", [(300000, 5000, 1.5), (70001, 3, 0.0), (1000, 4096, 0.0), (200000, 64, 3.0)])
+def test_k8_device_grouping_is_a_stable_counting_sort(faiss, n, nlist, skew):
+    """K8 (csr.cuh: histogram, column scan, stable scatter): after wb_ivf_finalize the storage order is exactly
+    numpy's stable argsort of the list numbers - skewed lists, empty lists, more lists than rows, several item blocks."""
+    from wise_b200 import _capi
+    L = _capi.lib()
+    d = 8
+    rng = np.random.default_rng(n + nlist)
+    if skew > 0:
+        w = 1.0 / np.arange(1, nlist + 1) ** skew
+        assign = rng.choice(nlist, size=n, p=w / w.sum()).astype(np.int32)
+    else:
+        assign = rng.integers(0, nlist, size=n).astype(np.int32)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    ids = rng.permutation(n).astype(np.int64) + 7
+    idx = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, nlist, faiss.METRIC_INNER_PRODUCT)
+    idx.set_centroids(O.unit_gaussian(nlist, d, 1))
+    for s in range(0, n, 50000):  # several adds
+        e = min(n, s + 50000)
+        _capi.check(L.wb_ivf_add_preassigned(idx._h, e - s, _capi.ptr(x[s:e]), _capi.ptr(ids[s:e]), _capi.ptr(assign[s:e])))
+    _capi.check(L.wb_ivf_finalize(idx._h))
+    xs, is_, as_ = idx._export(0, n, want_assign=True)
+    order = np.argsort(assign, kind="stable")
+    assert np.array_equal(as_, assign[order]) and np.array_equal(is_, ids[order]) and np.array_equal(xs, x[order])
+    off = np.empty(nlist + 1, np.int64)
+    grouped = C.c_int(0)
+    _capi.check(L.wb_ivf_list_offsets(idx._h, _capi.ptr(off), C.byref(grouped)))
+    assert grouped.value == 1
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(np.bincount(assign, minlength=nlist))]))
+    bad = assign.copy()
+    bad[5] = nlist  # an assignment outside [0, nlist) is reported, not scattered
+    idx2 = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, nlist, faiss.METRIC_INNER_PRODUCT)
+    idx2.set_centroids(O.unit_gaussian(nlist, d, 1))
+    _capi.check(L.wb_ivf_add_preassigned(idx2._h, 100, _capi.ptr(x[:100]), _capi.ptr(ids[:100]), _capi.ptr(bad[:100])))
+    assert L.wb_ivf_finalize(idx2._h) != 0 and b"outside" in L.wb_last_error()
+
+
+def test_misc_entry_points(faiss):
+    """wb_tf32_peak (the roofline denominator), pinned buffers, slot bookkeeping of the asynchronous add."""
+    from wise_b200 import _capi
+    L = _capi.lib()
+    tb, ts = C.c_double(), C.c_double()
+    _capi.check(L.wb_tf32_peak(0, 2000, 4, C.byref(tb), C.byref(ts)))
+    assert 300.0 < tb.value < 1400.0 and 300.0 < ts.value < 1400.0, (tb.value, ts.value)
+    d, n = 40, 1000
+    p_x, p_i = C.c_void_p(), C.c_void_p()
+    _capi.check(L.wb_pinned_alloc(n * d * 4, C.byref(p_x)))
+    _capi.check(L.wb_pinned_alloc(n * 8, C.byref(p_i)))
+    x = np.ctypeslib.as_array((C.c_float * (n * d)).from_address(p_x.value)).reshape(n, d)
+    ids = np.ctypeslib.as_array((C.c_int64 * n).from_address(p_i.value))
+    x[:] = O.unit_gaussian(n, d, 3)
+    ids[:] = np.arange(n) * 2
+    idx = faiss.IndexIDMap(faiss.IndexFlatIP(d))
+    assert L.wb_add_with_ids_pinned(idx._h, n, p_x, p_i, 8) != 0  # slot out of range
+    _capi.check(L.wb_add_with_ids_pinned(idx._h, n, p_x, p_i, 3))
+    _capi.check(L.wb_add_slot_wait(idx._h, 3))
+    _capi.check(L.wb_add_slot_wait(idx._h, 5))  # nothing pending: returns at once
+    _capi.check(L.wb_sync(idx._h))
+    D, I = idx.search(x[:3].copy(), 1)
+    assert I[:, 0].tolist() == [0, 2, 4]
+    _capi.check(L.wb_pinned_free(p_x))
+    _capi.check(L.wb_pinned_free(p_i))
