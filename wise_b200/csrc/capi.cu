@@ -605,6 +605,9 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     // Batches above 128 queries run their filter epochs in 256-query blocks on the SS kernel (gemm_ss.cuh): half as many
     // passes over the rows and 1.5x fewer L2 bytes per MAC than 128-query blocks.
     const bool use_f2 = BN >= 128 && filter && use2 && nq > 128 && env_int("WB_GEMM_F2", 1) != 0;
+    // a single block of 65..128 queries: the same SS kernel with 64 queries per CTA (one pass over the rows, HBM-bound)
+    const bool use_f2h = BN >= 128 && filter && use2 && nq <= 128 && env_int("WB_GEMM_F2", 1) != 0 &&
+                         env_int("WB_GEMM_F2H", 1) != 0;
     const int nqb2 = (int)((nq + kF2BN - 1) / kF2BN);
     const int nq_pad = use_f2 ? nqb2 * kF2BN : nqb * kGemmBN;  // thresholds / margins of padding queries: +inf / 0
     TRY(h->gimg.ensure((size_t)nqb * nchunks * kGemmBBytes));
@@ -626,8 +629,15 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
     if (use_f2) {
         TRY(h->gimg2.ensure((size_t)nqb2 * 2 * nchunks * kF2BBytes));
         const int64_t n4 = (int64_t)nqb2 * 2 * nchunks * 8 * kF2Half;
-        image_queries_f2_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb2,
-                                                                             h->gimg2.as<float>());
+        image_queries_f2_kernel<128><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb2,
+                                                                                  h->gimg2.as<float>());
+        CK(cudaGetLastError());
+        h->launches++;
+    } else if (use_f2h) {
+        TRY(h->gimg2.ensure((size_t)nqb * 2 * nchunks * F2Cfg<64>::kBBytes));
+        const int64_t n4 = (int64_t)nqb * 2 * nchunks * 8 * 64;
+        image_queries_f2_kernel<64><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(q_ld, (int)nq, ld, nchunks, nqb,
+                                                                                 h->gimg2.as<float>());
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -743,7 +753,7 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
             if (use_f2 && one_term) {  // 256-query blocks, both operands from shared memory
                 static thread_local bool a3[64] = {};
                 if (dev >= 64 || !a3[dev]) {
-                    CK(cudaFuncSetAttribute(filter2_topk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                    CK(cudaFuncSetAttribute(filter2_topk_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)kF2SmemBytes));
                     if (dev < 64) a3[dev] = true;
                 }
@@ -752,7 +762,20 @@ static int run_flat_gemm_t(wb_index* h, const float* rows, int64_t nrows, const 
                 g2.bimg = h->gimg2.as<float>();
                 const int64_t ntp = ((r1 - r0 + kGemmBM - 1) / kGemmBM + 1) / 2;
                 const unsigned grid3 = 2u * (unsigned)std::min<int64_t>(ntp * nqb2, h->sm_count / 2);
-                filter2_topk_kernel<false, false><<<grid3, kF2Threads, kF2SmemBytes, st>>>(tmap, g2);
+                filter2_topk_kernel<128, false, false><<<grid3, kF2Threads, kF2SmemBytes, st>>>(tmap, g2);
+                launched = true;
+            } else if (use_f2h && one_term) {
+                static thread_local bool a5[64] = {};
+                if (dev >= 64 || !a5[dev]) {
+                    CK(cudaFuncSetAttribute(filter2_topk_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)F2Cfg<64>::kSmemBytes));
+                    if (dev < 64) a5[dev] = true;
+                }
+                GemmParams g2 = g;
+                g2.bimg = h->gimg2.as<float>();
+                const int64_t ntp = ((r1 - r0 + kGemmBM - 1) / kGemmBM + 1) / 2;
+                const unsigned grid3 = 2u * (unsigned)std::min<int64_t>(ntp * nqb, h->sm_count / 2);
+                filter2_topk_kernel<64, false, false><<<grid3, kF2Threads, F2Cfg<64>::kSmemBytes, st>>>(tmap, g2);
                 launched = true;
             }
         }
@@ -861,7 +884,7 @@ static int run_assign_gemm(wb_index* h, const float* x_ld, int64_t n, int32_t* a
         int dev = 0;
         CK(cudaGetDevice(&dev));
         if (dev >= 64 || !a4[dev]) {
-            CK(cudaFuncSetAttribute(filter2_topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            CK(cudaFuncSetAttribute(filter2_topk_kernel<128, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)kF2SmemBytes));
             if (dev < 64) a4[dev] = true;
         }
@@ -875,7 +898,7 @@ static int run_assign_gemm(wb_index* h, const float* x_ld, int64_t n, int32_t* a
         g.assign_out = assign_out;
         g.best_out = best_out;
         const int64_t ntp = ((n + kGemmBM - 1) / kGemmBM + 1) / 2;
-        filter2_topk_kernel<true, false><<<2u * (unsigned)std::min<int64_t>(ntp, h->sm_count / 2), kF2Threads, kF2SmemBytes, st>>>(tm, g);
+        filter2_topk_kernel<128, true, false><<<2u * (unsigned)std::min<int64_t>(ntp, h->sm_count / 2), kF2Threads, kF2SmemBytes, st>>>(tm, g);
         CK(cudaGetLastError());
         h->launches += 2;
         h->gemm_launches++;

@@ -23,30 +23,42 @@
 
 namespace wb {
 
-constexpr int kF2Half = 128;                      // queries per CTA; the pair's block is 256
+// NH = queries per CTA (the pair's block is 2 * NH): 128 for batches above 128 queries and for the k-means assignment,
+// 64 for a single block of 65..128 queries (one pass over the rows, HBM-bound: the TS kernel's transform + TMEM stores
+// on top of N = 128 MMAs made that block tensor/TMEM-bound at the power-capped clock).
+template <int NH>
+struct F2Cfg {
+    static constexpr int kBN = 2 * NH;
+    static constexpr int kBBytes = NH * kGemmBK * 4;  // NH queries x 32 floats, no-swizzle core-matrix layout
+    static constexpr int kStageBytes = kGemmABytes + kBBytes;
+    static constexpr int kStages = NH >= 128 ? 6 : 8;
+    static constexpr int kNumBars = 3 * kStages + 4;
+    static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + kNumBars * 8 + 16 + 2 * kBN * 4;
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
+    static_assert(2 * kBN <= kTmemCols, "two accumulators in tensor memory");
+};
+constexpr int kF2Half = 128;
 constexpr int kF2BN = 2 * kF2Half;
-constexpr int kF2BBytes = kF2Half * kGemmBK * 4;  // 16 KB: 128 queries x 32 floats, no-swizzle core-matrix layout
-constexpr int kF2StageBytes = kGemmABytes + kF2BBytes;
-constexpr int kF2Stages = 6;
+constexpr int kF2BBytes = F2Cfg<128>::kBBytes;
+constexpr int kF2StageBytes = F2Cfg<128>::kStageBytes;
 constexpr int kF2Threads = 384;
 constexpr int kF2EpiThreads = 256;
-constexpr int kF2NumBars = 3 * kF2Stages + 4;
-constexpr size_t kF2SmemBytes = 1024 + (size_t)kF2Stages * kF2StageBytes + kF2NumBars * 8 + 16 + 2 * kF2BN * 4;
-static_assert(kF2SmemBytes <= 232448, "shared memory budget");
+constexpr size_t kF2SmemBytes = F2Cfg<128>::kSmemBytes;
 
-// Query image of the SS kernel: image[qb][half][chunk][k16 = 0..7][n = 0..127][4 floats] - raw fp32 (the tensor core
+// Query image of the SS kernel: image[qb][half][chunk][k16 = 0..7][n = 0..NH-1][4 floats] - raw fp32 (the tensor core
 // uses the tf32 part), K-major core matrices: 8 queries x 16 B are 128 contiguous bytes, SBO = 128 B between
-// 8-query groups, LBO = 128 * 16 B between 16-byte k columns.
+// 8-query groups, LBO = NH * 16 B between 16-byte k columns.
+template <int NH = 128>
 __global__ void image_queries_f2_kernel(const float* q, int nq, int ld, int nchunks, int nqb, float* img) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one float4 per thread
-    const int64_t total = (int64_t)nqb * 2 * nchunks * 8 * kF2Half;
+    const int64_t total = (int64_t)nqb * 2 * nchunks * 8 * NH;
     if (i >= total) return;
-    const int n = (int)(i % kF2Half);
-    const int k16 = (int)((i / kF2Half) % 8);
-    const int chunk = (int)((i / (kF2Half * 8)) % nchunks);
-    const int half = (int)((i / ((int64_t)kF2Half * 8 * nchunks)) % 2);
-    const int qb = (int)(i / ((int64_t)kF2Half * 8 * nchunks * 2));
-    const int qi = qb * kF2BN + half * kF2Half + n;
+    const int n = (int)(i % NH);
+    const int k16 = (int)((i / NH) % 8);
+    const int chunk = (int)((i / (NH * 8)) % nchunks);
+    const int half = (int)((i / ((int64_t)NH * 8 * nchunks)) % 2);
+    const int qb = (int)(i / ((int64_t)NH * 8 * nchunks * 2));
+    const int qi = qb * 2 * NH + half * NH + n;
     const int col = chunk * kGemmBK + k16 * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (qi < nq) {
@@ -80,18 +92,23 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
 // all centroid blocks of its row tiles back to back and every row keeps a running (max, lowest index) in the
 // epilogue registers - plain TF32 scores (SURVEY.md 8d allows it for training: "argmax only"), so two centroids
 // whose scores differ by less than ~2e-3 |x||c| may swap.  Add-time assignment stays on the exact 3xTF32 kernel.
-template <bool ARGMAX = false, bool TIMING_ONLY = false>
+template <int NH = 128, bool ARGMAX = false, bool TIMING_ONLY = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF2Threads, 1)
 filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p) {
+    using Cfg = F2Cfg<NH>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kStageBytes = Cfg::kStageBytes;
+    constexpr int kBBytes = Cfg::kBBytes;
+    constexpr int kBN = Cfg::kBN;
     extern __shared__ __align__(1024) unsigned char smem_f2[];
     unsigned char* stages = smem_f2 + ((1024u - (smem_u32(smem_f2) & 1023u)) & 1023u);  // same offset in both CTAs
-    uint64_t* full = reinterpret_cast<uint64_t*>(stages + (size_t)kF2Stages * kF2StageBytes);  // my rows + my half image landed
-    uint64_t* peer_full = full + kF2Stages;   // leader only: the peer's stage landed
-    uint64_t* empty = peer_full + kF2Stages;  // both: the MMAs that read this stage have retired (multicast commit)
-    uint64_t* d_full = empty + kF2Stages;     // both: accumulator ready (multicast commit)
+    uint64_t* full = reinterpret_cast<uint64_t*>(stages + (size_t)kStages * kStageBytes);  // my rows + my half image landed
+    uint64_t* peer_full = full + kStages;   // leader only: the peer's stage landed
+    uint64_t* empty = peer_full + kStages;  // both: the MMAs that read this stage have retired (multicast commit)
+    uint64_t* d_full = empty + kStages;     // both: accumulator ready (multicast commit)
     uint64_t* d_empty = d_full + 2;           // leader only: both epilogues drained the accumulator (16 warp arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
-    float* thr_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256], 16-byte aligned
+    float* thr_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][2 * NH], 16-byte aligned
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t crank = cluster_ctarank();
@@ -123,7 +140,7 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
     };
 
     if (tid == 0) {
-        for (int s = 0; s < kF2Stages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&peer_full[s], 1);
             mbar_init(&empty[s], 1);
@@ -155,17 +172,17 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
             int qb;
             work_at(it, tile, qb);
             const int row0 = (int)(p.row_begin + tile * kGemmBM);  // may be past row_end: TMA zero-fills
-            const float* bsrc = p.bimg + (size_t)(2 * qb + (int)crank) * p.nchunks * (kF2BBytes / 4);
+            const float* bsrc = p.bimg + (size_t)(2 * qb + (int)crank) * p.nchunks * (kBBytes / 4);
             for (int c = 0; c < p.nchunks; ++c) {
                 mbar_wait(&empty[s], ph ^ 1u);
                 if (elect_one_sync()) {
-                    unsigned char* st = stages + (size_t)s * kF2StageBytes;
-                    mbar_arrive_expect_tx(&full[s], kF2StageBytes);
+                    unsigned char* st = stages + (size_t)s * kStageBytes;
+                    mbar_arrive_expect_tx(&full[s], kStageBytes);
                     tma_load_2d(st, &tmap, c * kGemmBK, row0, &full[s]);
-                    bulk_g2s(st + kGemmABytes, bsrc + (size_t)c * (kF2BBytes / 4), kF2BBytes, &full[s]);
+                    bulk_g2s(st + kGemmABytes, bsrc + (size_t)c * (kBBytes / 4), kBBytes, &full[s]);
                 }
                 __syncwarp();
-                if (++s == kF2Stages) { s = 0; ph ^= 1u; }
+                if (++s == kStages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1 && !leader) {
@@ -177,14 +194,14 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
                 mbar_wait(&full[s], ph);
                 if (elect_one_sync()) mbar_arrive_cluster(&peer_full[s], 0);
                 __syncwarp();
-                if (++s == kF2Stages) { s = 0; ph ^= 1u; }
+                if (++s == kStages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // =============================== leader: MMA issuer for the pair =============================
-        constexpr uint32_t idesc = umma_idesc_tf32(2 * kGemmBM, kF2BN);
+        constexpr uint32_t idesc = umma_idesc_tf32(2 * kGemmBM, kBN);
         const uint64_t adesc0 = umma_smem_desc_sw128(smem_u32(stages));
-        const uint64_t bdesc0 = umma_smem_desc(smem_u32(stages + kGemmABytes), kF2Half * 16, 128);
+        const uint64_t bdesc0 = umma_smem_desc(smem_u32(stages + kGemmABytes), NH * 16, 128);
         const uint32_t a_lo0 = (uint32_t)adesc0, a_hi = (uint32_t)(adesc0 >> 32);
         const uint32_t b_lo0 = (uint32_t)bdesc0, b_hi = (uint32_t)(bdesc0 >> 32);
         int s = 0;
@@ -194,32 +211,32 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
         for (int64_t it = 0; it < my_work; ++it) {
             mbar_wait(&d_empty[buf], dph ^ 1u);  // both epilogues have drained this accumulator
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kF2BN);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kBN);
             for (int c = 0; c < p.nchunks; ++c) {
                 mbar_wait(&full[s], ph);
                 mbar_wait(&peer_full[s], ph);
                 tc_fence_after();
                 if (elect_one_sync()) {
-                    const uint32_t so = (uint32_t)s * (uint32_t)(kF2StageBytes >> 4);
+                    const uint32_t so = (uint32_t)s * (uint32_t)(kStageBytes >> 4);
 #pragma unroll
                     for (int j = 0; j < kGemmBK / 8; ++j) {
                         // one k-step = 8 tf32 = 32 B: inside the 128-byte swizzle atom for A, two 16-byte k columns for B
                         const uint64_t da = desc_from_words(a_lo0 + so + (uint32_t)(j * 2), a_hi);
-                        const uint64_t db = desc_from_words(b_lo0 + so + (uint32_t)((j * 2 * kF2Half * 16) >> 4), b_hi);
+                        const uint64_t db = desc_from_words(b_lo0 + so + (uint32_t)((j * 2 * NH * 16) >> 4), b_hi);
                         umma_tf32_ss_2cta(d_tmem, da, db, idesc, (c | j) != 0);
                     }
                     umma_commit_2cta(&empty[s]);
                     if (c == p.nchunks - 1) umma_commit_2cta(&d_full[buf]);
                 }
                 __syncwarp();
-                if (++s == kF2Stages) { s = 0; ph ^= 1u; }
+                if (++s == kStages) { s = 0; ph ^= 1u; }
             }
             if (++buf == 2) { buf = 0; dph ^= 1u; }
         }
     } else if (warp >= 4) {
         // =============================== epilogue (this CTA's 128 rows x 256 queries) ================
         const int quarter = warp & 3;
-        const int chalf = (warp - 4) >> 2;  // which 128 of the 256 query columns
+        const int chalf = (warp - 4) >> 2;  // which half (NH) of the block's 2 * NH query columns
         const int etid = tid - 4 * 32;      // 0..255
         int buf = 0;
         uint32_t dph = 0;
@@ -232,7 +249,7 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
             const int64_t row = p.row_begin + tile * kGemmBM + quarter * 32 + lane;
             const bool row_ok = row < p.row_end;
             if constexpr (!ARGMAX) {
-                thr_s[buf * kF2BN + etid] = p.thr[qb * kF2BN + etid] - p.margin[qb * kF2BN + etid];  // +inf for padding
+                if (etid < kBN) thr_s[buf * kBN + etid] = p.thr[qb * kBN + etid] - p.margin[qb * kBN + etid];  // +inf for padding
                 named_bar_sync(kBarEpilogue, kF2EpiThreads);
             } else if (qb == 0) {
                 best = -INFINITY;
@@ -240,16 +257,16 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
             }
             mbar_wait(&d_full[buf], dph);
             tc_fence_after();
-            const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kF2BN + chalf * kF2Half);
-            const float* thr_w = thr_s + buf * kF2BN + chalf * kF2Half;
+            const uint32_t td = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kBN + chalf * NH);
+            const float* thr_w = thr_s + buf * kBN + chalf * NH;
 #pragma unroll 1
-            for (int cb = 0; cb < kF2Half / 32; ++cb) {
+            for (int cb = 0; cb < NH / 32; ++cb) {
                 uint32_t v[32];
                 tmem_ld32(td + cb * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if constexpr (TIMING_ONLY) continue;
                 if constexpr (ARGMAX) {
-                    const int c0 = qb * kF2BN + chalf * kF2Half + cb * 32;
+                    const int c0 = qb * kBN + chalf * NH + cb * 32;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float sc = __uint_as_float(v[j]);
@@ -279,7 +296,7 @@ filter2_topk_kernel(const __grid_constant__ CUtensorMap tmap, const GemmParams p
                     const bool pass = row_ok && sc > thr_w[cb * 32 + j];
                     const unsigned m = __ballot_sync(0xffffffffu, pass);
                     if (m) {
-                        const int qi = qb * kF2BN + chalf * kF2Half + cb * 32 + j;  // < nq: padded queries have thr = +inf
+                        const int qi = qb * kBN + chalf * NH + cb * 32 + j;  // < nq: padded queries have thr = +inf
                         int base = 0;
                         if (lane == (__ffs(m) - 1)) base = atomicAdd(&p.cnt[qi], __popc(m));
                         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
