@@ -124,29 +124,58 @@ __host__ __device__ __forceinline__ int pow2_ceil(int v) {
 
 // ---- bitonic sort of `nlists` arrays of P (power of two) keys, descending -------------------
 // Executed by NT threads that share barrier `bar_id` (bar_id < 0 => __syncthreads()).
+// Thread i owns the compare-exchange j = i mod (P/2) of list i / (P/2).  For strides <= 32 the 32 consecutive j of a
+// warp touch only the warp's own 64 keys, so those steps need a __syncwarp, not a block barrier: a 1024-key sort takes
+// 15 block barriers instead of 55, a 256-key flush 6 instead of 36 (each barrier costs a 256-thread group ~100 cycles;
+// the sorts sit on the tail of every scan and on every threshold flush).
+template <int NT>
+__device__ __forceinline__ void bitonic_block_sync(int bar_id) {
+    if (bar_id < 0) __syncthreads();
+    else named_bar_sync(bar_id, NT);
+}
+
 template <int NT>
 __device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int P, int nlists, int tid, int bar_id) {
+    static_assert(NT % 32 == 0, "whole warps");
     const int half = P >> 1;
     const int lg_half = 31 - __clz(half);  // P is a power of two: no integer division in the loops
     const int total = nlists << lg_half;
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = tid; i < total; i += NT) {
-                const int l = i >> lg_half;
-                const int j = i & (half - 1);
-                const int pos = 2 * j - (j & (stride - 1));
-                uint64_t* base = keys + ((size_t)l << (lg_half + 1));
-                const uint64_t a = base[pos], b = base[pos + stride];
-                const bool desc = ((pos & size) == 0);
-                if ((a < b) == desc) {
-                    base[pos] = b;
-                    base[pos + stride] = a;
-                }
+    auto step = [&](int size, int stride) {
+        for (int i = tid; i < total; i += NT) {
+            const int l = i >> lg_half;
+            const int j = i & (half - 1);
+            const int pos = 2 * j - (j & (stride - 1));
+            uint64_t* base = keys + ((size_t)l << (lg_half + 1));
+            const uint64_t a = base[pos], b = base[pos + stride];
+            const bool desc = ((pos & size) == 0);
+            if ((a < b) == desc) {
+                base[pos] = b;
+                base[pos + stride] = a;
             }
-            if (bar_id < 0) __syncthreads();
-            else named_bar_sync(bar_id, NT);
         }
+    };
+    if (half < 32) {  // tiny lists: a warp's pairs are not confined to 64 keys of one list - plain scheme
+        for (int size = 2; size <= P; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                step(size, stride);
+                bitonic_block_sync<NT>(bar_id);
+            }
+        return;
     }
+    // (the loop trip count is warp-uniform: total is a multiple of 32 and NT a multiple of 32)
+    for (int size = 2; size <= P; size <<= 1) {
+        int stride = size >> 1;
+        for (; stride > 32; stride >>= 1) {  // pairs cross warps
+            step(size, stride);
+            bitonic_block_sync<NT>(bar_id);
+        }
+        for (; stride > 0; stride >>= 1) {   // pairs stay inside the warp's 64 keys
+            step(size, stride);
+            __syncwarp();
+        }
+        if (size >= 64) bitonic_block_sync<NT>(bar_id);  // the next size starts with a stride >= 64 (or the sort is done)
+    }
+    if (P < 64) bitonic_block_sync<NT>(bar_id);
 }
 
 }  // namespace wb
