@@ -345,3 +345,47 @@ def test_gemm_score_audit_repeated(faiss, monkeypatch):
         true = np.einsum('qkd,qd->qk', xb[I].astype(np.float64), xq.astype(np.float64))
         assert np.abs(true - D).max() <= 1e-5, (trial, float(np.abs(true - D).max()))
         O.compare_topk(D, I, Dr, Ir, band=4e-6)
+
+
+def test_winners_clustered_in_a_few_partial_lists(faiss):
+    """The merge of sorted partial lists (scan tail, K3, exchange) looks at the best few entries of every list first and
+    then follows the lists that reach deeper (binary search for the prefix that beats the threshold).  Here ALL winners
+    sit in 100 consecutive rows (3-4 row groups, i.e. 3-4 of the 148 per-CTA lists), and in one part of an 8-part merge."""
+    import torch
+    from wise_b200 import _capi
+    L = _capi.lib()
+    n, d, k = 200000, 64, 100
+    xb = O.unit_gaussian(n, d, 5)
+    q = O.unit_gaussian(2, d, 6)
+    rng = np.random.default_rng(7)
+    for j, start in enumerate((5000, 150000)):  # rows close to query j: all of its top-100
+        near = q[j] + 0.05 * rng.standard_normal((100, d)).astype(np.float32)
+        xb[start:start + 100] = near / np.linalg.norm(near, axis=1, keepdims=True)
+    ids = np.arange(n, dtype=np.int64) + 11
+    idx = _flat(faiss, xb, ids)
+    D, I = idx.search(q, k)
+    Dr, Ir = O.flat_search(xb, q, k, ids)
+    O.compare_topk(D, I, Dr, Ir)
+    assert set(I[0]) == set(range(5011, 5111)) and set(I[1]) == set(range(150011, 150111))
+    D1, I1 = idx.search(q[:1], k)  # batch 1: the fused tail of the one-query scan
+    O.compare_topk(D1, I1, Dr[:1], Ir[:1])
+    # 8 sorted parts, the whole answer in part 3 (the shape of the multi-GPU exchange when one shard holds the winners)
+    G, nq = 8, 3
+    Dp = torch.full((G, nq, k), 0.0, device="cuda")
+    Ip = torch.zeros((G, nq, k), dtype=torch.int64, device="cuda")
+    for g in range(G):
+        base = 0.9 if g == 3 else 0.5
+        Dp[g] = (base - 1e-3 * torch.arange(k, device="cuda").float() - 1e-5 * g).expand(nq, k)
+        Ip[g] = (g * 1000 + torch.arange(k, device="cuda")).expand(nq, k)
+    Dm = torch.empty(nq, k, device="cuda"); Im = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _capi.check(L.wb_merge_topk_dev(0, nq, k, G, Dp.data_ptr(), Ip.data_ptr(), Dm.data_ptr(), Im.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(Im, Ip[3]) and torch.equal(Dm, Dp[3])
+    # two parts that interleave entry by entry
+    Dp2 = torch.stack([(0.9 - 2e-3 * torch.arange(k, device="cuda").float()).expand(nq, k),
+                       (0.899 - 2e-3 * torch.arange(k, device="cuda").float()).expand(nq, k)]).contiguous()
+    Ip2 = torch.stack([(torch.arange(k, device="cuda") * 2).expand(nq, k), (torch.arange(k, device="cuda") * 2 + 1).expand(nq, k)]).contiguous()
+    _capi.check(L.wb_merge_topk_dev(0, nq, k, 2, Dp2.data_ptr(), Ip2.data_ptr(), Dm.data_ptr(), Im.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert Im[0].tolist() == list(range(k))

@@ -117,12 +117,21 @@ __device__ __forceinline__ bool block_select_topk_lists(uint64_t* buf, int S, in
     sel_sync<NT>(bar_id);
     const uint64_t thr = buf[k - 1];
     for (int l = tid; l < nlists; l += NT) {
-        for (int r = j0; r < k; ++r) {
-            const uint64_t key = load(l, r);
-            if (!(key > thr)) break;  // sorted list: nothing below can pass either
-            const int slot = atomicAdd(cnt, 1);
-            if (slot < qcap) buf[k + slot] = key;
+        // The entries of a sorted list that beat thr are a prefix [j0, e).  Almost always it is empty (one load).  When
+        // the winners cluster in a few lists (an IVF query whose best lists were scanned by a few CTAs, a shard that
+        // holds most of the global top-k) e is found by binary search - 7 dependent loads instead of up to k - and the
+        // prefix is copied with independent loads.
+        if (!(load(l, j0) > thr)) continue;
+        int lo = j0 + 1, hi = k;  // every r < lo beats thr; no r >= hi does
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (load(l, mid) > thr) lo = mid + 1;
+            else hi = mid;
         }
+        const int c = lo - j0;
+        const int slot0 = atomicAdd(cnt, c);
+        if (slot0 + c <= qcap)
+            for (int r = j0; r < lo; ++r) buf[k + slot0 + (r - j0)] = load(l, r);
     }
     sel_sync<NT>(bar_id);
     const int c = *cnt;

@@ -59,7 +59,11 @@ class PinnedRing:
 def add_store_pipelined(index, store) -> int:
     """index.add_with_ids over every shard of an un-shuffled WebdatasetStore (already enable_read()),
     in shard order = the reference's insertion order.  Returns the number of rows added.
-    Shards the C++ reader does not understand go through the python reader (synchronously, same order)."""
+    Shards the C++ reader does not understand go through the python reader (synchronously, same order).
+
+    Threads: the helper thread only decodes and calls wb_add_slot_wait (an event wait on a slot the main thread is not
+    using); every call that changes the index (wb_add_with_ids_pinned, add_with_ids) is made by the calling thread, in
+    shard order, and the future hand-off orders the two."""
     L = _capi.lib()
     files = list(store.shard_files())
     rows_by = getattr(store, "_shard_rows", {})
