@@ -9,7 +9,8 @@ A "step" is one search of a batch of B queries (default B=1: the bandwidth-bound
 reference serves, /root/reference/api/routes.py:1407) over the whole database:
   value    QPS with queries already in HBM (wb_search_dev), CUDA events on the launching stream
   e2e      QPS through the public API `index.search(numpy, k)` with pinned HOST buffers: H2D of
-           the queries and D2H of (D, I) inside the timed region
+           the queries and D2H of (D, I) inside the timed region (result sets up to 64 KB are written by the
+           emitting kernel straight into pinned host memory over PCIe, larger ones are copied; same bytes either way)
   roofline achieved = N*d*4 bytes / scan-kernel duration (events inside the library, same stream)
            vs the measured copy bandwidth in MEASURED_PEAKS.json
   parity_check  the (D, I) of the LAST timed step verified after the timed region on every rank against an fp64
@@ -669,7 +670,9 @@ def run_ours(a):
                       "exchange": "NVLink peer-memory mailbox kernel (no NCCL on the search path)" if world > 1 else "none"},
             "roofline": roofline_of(a.batch, scan_ms),
             "e2e": {"value": a.batch / (e2e_ms / 1e3), "unit": "queries/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": a.batch * a.dim * 4, "d2h_bytes_per_step": a.batch * a.k * 12},
+                    "h2d_bytes_per_step": a.batch * a.dim * 4, "d2h_bytes_per_step": a.batch * a.k * 12,
+                    "d2h_how": "kernel stores into pinned host memory" if a.batch * a.k * 12 <= 65536
+                               and os.environ.get("WB_DIRECT_RESULTS", "1") != "0" else "cudaMemcpyAsync"},
             "gpu_launches": launches, "clocks": clocks, "parity_check": parity,
         }
         if sweep:

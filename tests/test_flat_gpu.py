@@ -389,3 +389,35 @@ def test_winners_clustered_in_a_few_partial_lists(faiss):
     _capi.check(L.wb_merge_topk_dev(0, nq, k, 2, Dp2.data_ptr(), Ip2.data_ptr(), Dm.data_ptr(), Im.data_ptr(), st))
     torch.cuda.synchronize()
     assert Im[0].tolist() == list(range(k))
+
+
+@pytest.mark.parametrize("nq,force_gemm", [(1, False), (3, False), (16, True), (300, True)])
+def test_nan_rows_and_nan_queries_are_never_returned(faiss, monkeypatch, nq, force_gemm):
+    """faiss keeps its result heaps with `if (C::cmp(simi[0], ip))` (a float '<'): a NaN score is never inserted, so
+    rows with a NaN component never surface and a NaN query returns the empty (-FLT_MAX, -1) row.  The kernels compare
+    floats against their thresholds before they build a key, which gives the same rule; a store with a few corrupt
+    embeddings must answer every other query exactly as if those rows were absent."""
+    if force_gemm:
+        monkeypatch.setenv("WB_GEMM_FORCE", "1")
+    n, d, k = 60000, 256, 50
+    xb = O.unit_gaussian(n, d, 77)
+    xq = O.unit_gaussian(nq, d, 78)
+    bad = np.array([0, 17, 4096, 31337, n - 1])
+    xb[bad, 5] = np.nan
+    xb[bad[1], :] = np.nan
+    ids = np.arange(n, dtype=np.int64) * 3 + 1
+    idx = _flat(faiss, xb, ids)
+    clean = np.setdiff1d(np.arange(n), bad)
+    Dr, Ir = O.flat_search(xb[clean], xq, k, ids[clean])
+    D, I = idx.search(xq, k)
+    if force_gemm:
+        epochs, fallbacks = _gemm_stats(idx)
+        assert epochs >= 1 and fallbacks == 0
+    O.compare_topk(D, I, Dr, Ir, band=4e-6 if force_gemm else O.NEAR_TIE_BAND)
+    assert not np.isin(I, ids[bad]).any() and np.isfinite(D).all()
+    xq2 = xq.copy()
+    xq2[0, 3] = np.nan  # a NaN query: every score is NaN, nothing is ever inserted
+    D2, I2 = idx.search(xq2, k)
+    assert np.all(I2[0] == -1) and np.all(D2[0] == O.NEG_FLT_MAX)
+    if nq > 1:
+        O.compare_topk(D2[1:], I2[1:], Dr[1:], Ir[1:], band=4e-6 if force_gemm else O.NEAR_TIE_BAND)

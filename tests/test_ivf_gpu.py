@@ -351,3 +351,40 @@ def test_misc_entry_points(faiss):
     assert I[:, 0].tolist() == [0, 2, 4]
     _capi.check(L.wb_pinned_free(p_x))
     _capi.check(L.wb_pinned_free(p_i))
+
+
+@pytest.mark.parametrize("nq", [1, 40])
+def test_ivf_nan_rows_are_stored_but_never_returned(faiss, nq):
+    """Same float-compare rule as the flat index (faiss heaps never insert a NaN score).  faiss's add_core drops a row
+    whose coarse label is -1 while still counting it in ntotal; here such a row lands in list 0 and no search can
+    return it - the observable behaviour (ntotal, results) is the same."""
+    n, d, nlist, k = 30000, 128, 64, 20
+    xb = O.clustered_unit(n, d, 2 * nlist, 60)
+    xq = O.clustered_unit(nq, d, 2 * nlist, 61)
+    cent = O.kmeans_init(xb, nlist)
+    bad = np.array([3, 700, 15000, n - 2])
+    xb[bad, 9] = np.nan
+    ids = np.arange(n, dtype=np.int64) * 7
+    idx = _ivf(faiss, xb, ids, cent)
+    assert idx.ntotal == n
+    _, _, ga = idx._export(0, n, want_assign=True)
+    clean = np.setdiff1d(np.arange(n), bad)
+    for nprobe in (4, 64):
+        idx.nprobe = nprobe
+        D, I = idx.search(xq, k)
+        Dr, Ir = O.ivf_search(xb[clean], ids[clean], ga[clean].astype(np.int64), cent, xq, k, nprobe)
+        O.compare_topk(D, I, Dr, Ir)
+        assert not np.isin(I, ids[bad]).any() and np.isfinite(D).all()
+        xq2 = xq.copy()
+        xq2[-1, 0] = np.nan  # a NaN query has no best centroid: it probes nothing and returns the empty row
+        D2, I2 = idx.search(xq2, k)
+        assert np.all(I2[-1] == -1) and np.all(D2[-1] == O.NEG_FLT_MAX)
+        if nq > 1:
+            O.compare_topk(D2[:-1], I2[:-1], Dr[:-1], Ir[:-1])
+    # faiss Clustering::train refuses a training set with NaN / Inf [faiss-upstream]
+    fresh = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, nlist, faiss.METRIC_INNER_PRODUCT)
+    with pytest.raises(RuntimeError, match="NaN"):
+        fresh.train(xb[:10000])  # rows 3 and 700 are corrupt (no subsampling below 256 points per centroid)
+    assert not fresh.is_trained
+    fresh.train(xb[clean][:10000])
+    assert fresh.is_trained

@@ -90,7 +90,7 @@ struct PinBuf {
         p = nullptr;
         cap = 0;
         const size_t want = std::max(bytes, (size_t)1 << 16);
-        CK(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        CK(cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable));  // kernels may write into it (UVA)
         cap = want;
         return 0;
     }
@@ -1116,7 +1116,7 @@ static int assign_rows(wb_index* h, const float* x_dev, int64_t n, int32_t* assi
     TRY(h->pI.ensure((size_t)n * sizeof(int64_t)));
     float* D = best_out ? best_out : h->pD.as<float>();
     TRY(run_flat_any(h, h->centroids, h->nlist, x_dev, n, 1, nullptr, D, h->pI.as<int64_t>(), st, false));
-    i64_to_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pI.as<int64_t>(), assign_out, n);
+    labels_to_lists_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pI.as<int64_t>(), assign_out, n);
     CK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -1284,7 +1284,8 @@ static int run_ivf_listmajor(wb_index* h, int64_t nq, const float* q_ld, int k, 
     TRY(h->lmF.ensure((size_t)max_items * 4));           // list of every work item
     TRY(h->lmG.ensure((size_t)nq * 4 + 64));             // shared thresholds + the work counter
     TRY(h->parts.ensure((size_t)npairs * k * sizeof(uint64_t)));
-    i64_to_i32_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(h->pI.as<int64_t>(), h->lmA.as<int32_t>(), npairs);
+    probes_to_pairs_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(h->pI.as<int64_t>(), h->lmA.as<int32_t>(), npairs, k,
+                                                                            h->parts.as<uint64_t>());
     CK(cudaGetLastError());
     TRY(device_csr(h, h->lmA.as<int32_t>(), npairs, nullptr, h->lmC.as<int64_t>(), h->lmB.as<uint32_t>(), nullptr, st, false));
     lm_item_count_kernel<<<(unsigned)((nlist + 255) / 256), 256, 0, st>>>(h->lmC.as<int64_t>(), nlist, 8, h->lmD.as<int64_t>());
@@ -1447,15 +1448,12 @@ static int stage_queries(wb_index* h, int64_t nq, const float* q, bool host, cud
 // `word_dev` (optional): one more device int fetched with the results (the exchange's time-out flag), so that reading
 // it costs no synchronisation of its own.
 static int fetch_results(wb_index* h, int64_t nq, int64_t k, const float* D_dev, const int64_t* I_dev, float* D_host,
-                         int64_t* I_host, cudaStream_t st, const int* word_dev = nullptr, int* word_host = nullptr) {
+                         int64_t* I_host, cudaStream_t st) {
     const size_t dbytes = (size_t)nq * k * sizeof(float), ibytes = (size_t)nq * k * sizeof(int64_t);
     PinBuf& pb = h->pin_o;
-    const bool staged = dbytes + ibytes <= kPinStageMax;
-    TRY(pb.ensure((staged ? dbytes + ibytes : 0) + 16));
-    unsigned char* stage = reinterpret_cast<unsigned char*>(pb.p);
-    int* word_stage = reinterpret_cast<int*>(stage + (staged ? ((dbytes + ibytes + 7) & ~(size_t)7) : 0));
-    if (word_dev) CK(cudaMemcpyAsync(word_stage, word_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (staged) {
+    if (dbytes + ibytes <= kPinStageMax) {
+        TRY(pb.ensure(dbytes + ibytes));
+        unsigned char* stage = reinterpret_cast<unsigned char*>(pb.p);
         CK(cudaMemcpyAsync(stage, I_dev, ibytes, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(stage + ibytes, D_dev, dbytes, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1466,7 +1464,28 @@ static int fetch_results(wb_index* h, int64_t nq, int64_t k, const float* D_dev,
         CK(cudaMemcpyAsync(I_host, I_dev, ibytes, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
-    if (word_dev && word_host) *word_host = *word_stage;
+    return 0;
+}
+
+// Small result sets skip the device buffer and its two D2H copies: the kernel that emits the final (D, I) rows writes
+// them straight into the pinned staging buffer (a few KB of posted PCIe writes), which the host reads after the
+// stream synchronisation.  At one query this takes ~10 us off a 60 us IVF call.
+constexpr size_t kDirectResultMax = (size_t)64 << 10;
+static bool direct_results(wb_index* h, int64_t nq, int64_t k) {
+    return (size_t)nq * k * 12 <= kDirectResultMax && env_int("WB_DIRECT_RESULTS", 1);
+}
+static int direct_result_buffers(wb_index* h, int64_t nq, int64_t k, float** D_pin, int64_t** I_pin) {
+    const size_t dbytes = (size_t)nq * k * sizeof(float), ibytes = (size_t)nq * k * sizeof(int64_t);
+    TRY(h->pin_o.ensure(dbytes + ibytes));
+    *I_pin = reinterpret_cast<int64_t*>(h->pin_o.p);
+    *D_pin = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(h->pin_o.p) + ibytes);
+    return 0;
+}
+static int finish_direct_results(int64_t nq, int64_t k, const float* D_pin, const int64_t* I_pin, float* D_host,
+                                 int64_t* I_host, cudaStream_t st) {
+    CK(cudaStreamSynchronize(st));
+    memcpy(I_host, I_pin, (size_t)nq * k * sizeof(int64_t));
+    memcpy(D_host, D_pin, (size_t)nq * k * sizeof(float));
     return 0;
 }
 
@@ -1489,6 +1508,13 @@ extern "C" int wb_search(wb_index* h, int64_t nq, const float* q_host, int64_t k
     cudaStream_t st = h->stream;
     const float* q = nullptr;
     TRY(stage_queries(h, nq, q_host, true, st, &q));
+    if (direct_results(h, nq, k)) {
+        float* Dp = nullptr;
+        int64_t* Ip = nullptr;
+        TRY(direct_result_buffers(h, nq, k, &Dp, &Ip));
+        TRY(search_dev_impl(h, nq, q, k, nprobe, Dp, Ip, st));
+        return finish_direct_results(nq, k, Dp, Ip, D_host, I_host, st);
+    }
     TRY(h->dbuf.ensure((size_t)nq * k * sizeof(float)));
     TRY(h->ibuf.ensure((size_t)nq * k * sizeof(int64_t)));
     TRY(search_dev_impl(h, nq, q, k, nprobe, h->dbuf.as<float>(), h->ibuf.as<int64_t>(), st));
@@ -1796,11 +1822,17 @@ extern "C" int wb_ivf_train(wb_index* h, int64_t n, const float* x_host, int nit
     int32_t* assign = nullptr;
     float* sums = nullptr;
     int64_t* counts = nullptr;
+    int* nonfinite = nullptr;
+    g_err.clear();  // the error path below reports a CUDA error only when no step has already described its failure
     do {
         if ((rc = (cudaMemcpyAsync(x, x_host, (size_t)n * d * 4, cudaMemcpyHostToDevice, st) != cudaSuccess))) break;
         if ((rc = (cudaMalloc(&assign, (size_t)n * 4) != cudaSuccess))) break;
         if ((rc = (cudaMalloc(&sums, (size_t)k * d * 4) != cudaSuccess))) break;
         if ((rc = (cudaMalloc(&counts, (size_t)k * 8) != cudaSuccess))) break;
+        // faiss Clustering::train: "input contains NaN's or Inf's" - checked on the device, read at the first sync
+        if ((rc = (cudaMalloc(&nonfinite, sizeof(int)) != cudaSuccess))) break;
+        if ((rc = (cudaMemsetAsync(nonfinite, 0, sizeof(int), st) != cudaSuccess))) break;
+        nonfinite_flag_kernel<<<(unsigned)(h->sm_count * 8), 256, 0, st>>>(x, n * (int64_t)d, nonfinite);
         // initial centroids: first k rows of the faiss-style random permutation, seed + 1
         std::mt19937 mt((uint32_t)(seed + 1));
         std::vector<int64_t> perm((size_t)n);
@@ -1822,6 +1854,12 @@ extern "C" int wb_ivf_train(wb_index* h, int64_t n, const float* x_host, int nit
             }
             h->launches++;
             if ((rc = (cudaStreamSynchronize(st) != cudaSuccess))) break;  // perm (host) is read by the copy above
+            int bad = 0;
+            if ((rc = (cudaMemcpy(&bad, nonfinite, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess))) break;
+            if (bad) {
+                rc = fail("input contains NaN's or Inf's");
+                break;
+            }
         }
         if (h->spherical) {
             renorm_rows_kernel<<<(unsigned)k, 256, 0, st>>>(h->centroids, h->ld, d);
@@ -1840,6 +1878,7 @@ extern "C" int wb_ivf_train(wb_index* h, int64_t n, const float* x_host, int nit
     cudaFree(assign);
     cudaFree(sums);
     cudaFree(counts);
+    cudaFree(nonfinite);
     if (rc) {
         if (g_err.empty()) fail("k-means training failed: %s", cudaGetErrorString(cudaGetLastError()));
         return 1;
@@ -1907,7 +1946,7 @@ struct wb_exchange {
     unsigned char* peers[kExchMaxWorld] = {};
     bool opened[kExchMaxWorld] = {};
     uint32_t seq = 0;       // sequence number of the last exchange that was LAUNCHED (all ranks advance in lockstep)
-    int* status = nullptr;  // device word raised by a kernel whose wait for the peers timed out
+    int* status = nullptr;  // pinned (device-visible) host word raised by a kernel whose wait for the peers timed out
     int64_t launches = 0;   // exchange_merge_kernel launches (the fused path needs none)
 };
 
@@ -1929,8 +1968,8 @@ extern "C" int wb_exch_create(int device, int rank, int world, int64_t max_queri
     ex->total_bytes = ex->region_bytes * 2 * world;
     CK(cudaMalloc(&ex->local, ex->total_bytes));
     CK(cudaMemset(ex->local, 0, ex->total_bytes));
-    CK(cudaMalloc(&ex->status, sizeof(int)));
-    CK(cudaMemset(ex->status, 0, sizeof(int)));
+    CK(cudaHostAlloc(&ex->status, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *ex->status = 0;
     CK(cudaDeviceSynchronize());
     ex->peers[rank] = ex->local;
     *out = ex;
@@ -1969,7 +2008,7 @@ extern "C" int wb_exch_free(wb_exchange* ex) {
     for (int r = 0; r < ex->world; ++r)
         if (ex->opened[r]) cudaIpcCloseMemHandle(ex->peers[r]);
     cudaFree(ex->local);
-    cudaFree(ex->status);
+    cudaFreeHost(ex->status);
     delete ex;
     return 0;
 }
@@ -2035,13 +2074,13 @@ extern "C" int wb_exch_merge_dev(wb_exchange* ex, int64_t nq, int64_t k, const f
 }
 
 // 1 when a kernel of this exchange gave up waiting for a peer (a rank that never launched): the results of that
-// search are invalid.  Reads the device word (synchronises with the kernels that wrote it only if the caller did).
+// search are invalid.  The word lives in pinned host memory that the kernels write through; it is current for every
+// kernel the caller has synchronised with.
 extern "C" int64_t wb_exch_launch_count(const wb_exchange* ex) { return ex ? ex->launches : -1; }
 
 extern "C" int wb_exch_status(wb_exchange* ex, int* timed_out) {
     if (!ex || !timed_out) return fail("NULL argument");
-    CK(cudaSetDevice(ex->device));
-    CK(cudaMemcpy(timed_out, ex->status, sizeof(int), cudaMemcpyDeviceToHost));
+    *timed_out = *reinterpret_cast<volatile int*>(ex->status);
     return 0;
 }
 
@@ -2163,11 +2202,18 @@ extern "C" int wb_exch_search(wb_index* h, wb_exchange* ex, int64_t nq, const fl
     cudaStream_t st = h->stream;
     const float* q = nullptr;
     TRY(stage_queries(h, nq, q_host, true, st, &q));
-    TRY(h->eD.ensure((size_t)nq * k * sizeof(float)));
-    TRY(h->eI.ensure((size_t)nq * k * sizeof(int64_t)));
-    TRY(exch_search_dev_impl(h, ex, nq, q, k, nprobe, h->eD.as<float>(), h->eI.as<int64_t>(), st));
-    int timed_out = 0;
-    TRY(fetch_results(h, nq, k, h->eD.as<float>(), h->eI.as<int64_t>(), D_host, I_host, st, ex->status, &timed_out));
-    if (timed_out) return fail("sharded search: a peer GPU did not join the exchange within 20 s (results invalid)");
+    if (direct_results(h, nq, k)) {
+        float* Dp = nullptr;
+        int64_t* Ip = nullptr;
+        TRY(direct_result_buffers(h, nq, k, &Dp, &Ip));
+        TRY(exch_search_dev_impl(h, ex, nq, q, k, nprobe, Dp, Ip, st));
+        TRY(finish_direct_results(nq, k, Dp, Ip, D_host, I_host, st));
+    } else {
+        TRY(h->eD.ensure((size_t)nq * k * sizeof(float)));
+        TRY(h->eI.ensure((size_t)nq * k * sizeof(int64_t)));
+        TRY(exch_search_dev_impl(h, ex, nq, q, k, nprobe, h->eD.as<float>(), h->eI.as<int64_t>(), st));
+        TRY(fetch_results(h, nq, k, h->eD.as<float>(), h->eI.as<int64_t>(), D_host, I_host, st));
+    }
+    if (*reinterpret_cast<volatile int*>(ex->status)) return fail("sharded search: a peer GPU did not join the exchange within 20 s (results invalid)");
     return 0;
 }

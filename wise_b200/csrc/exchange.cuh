@@ -37,7 +37,7 @@ struct ExchParams {
     size_t cap_entries;             // D/I capacity of a region
     float* D;                       // [nq][k] merged
     int64_t* I;
-    int* status;                    // device word: set to 1 when a wait timed out (results are then invalid)
+    int* status;                    // pinned host word: set to 1 when a wait timed out (results are then invalid)
 };
 
 __device__ __forceinline__ unsigned char* exch_region(const ExchParams& p, int owner, int buf, int sender) {
@@ -87,7 +87,7 @@ __device__ __forceinline__ void exch_push_wait_merge(const ExchParams& p, int64_
                 const unsigned long long now = global_ns();
                 if (t0 == 0) t0 = now;
                 else if (now - t0 > kExchTimeoutNs) {
-                    if (p.status) atomicExch(p.status, 1);
+                    if (p.status) *reinterpret_cast<volatile int*>(p.status) = 1;  // pinned host word
                     break;
                 }
             }

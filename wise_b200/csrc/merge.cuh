@@ -327,9 +327,31 @@ __global__ void iota_ids_kernel(int64_t* ids, int64_t start, int64_t n) {
     if (i < n) ids[i] = start + i;
 }
 
-__global__ void i64_to_i32_kernel(const int64_t* in, int32_t* out, int64_t n) {
+// *flag <- 1 when x[0..count) holds a NaN or an Inf (faiss Clustering::train refuses such a training set)
+__global__ void nonfinite_flag_kernel(const float* x, int64_t count, int* flag) {
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        bad |= !isfinite(x[i]);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 1;
+}
+
+// Coarse labels of added rows -> list numbers.  A row whose scores are all NaN has no best centroid (label -1; faiss
+// add_core leaves such a row out of every list but still counts it): it is filed under list 0, where no search can
+// return it (a NaN score never passes a threshold compare), so the store stays searchable.
+__global__ void labels_to_lists_kernel(const int64_t* labels, int32_t* out, int64_t n) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (int32_t)in[i];
+    if (i < n) out[i] = labels[i] < 0 ? 0 : (int32_t)labels[i];
+}
+
+// (query, probe slot) pairs of a batch -> list numbers for the list-major scan.  A slot without a list (-1: a NaN
+// query has no best centroids) gets an EMPTY result list - no work item will ever write it.
+__global__ void probes_to_pairs_kernel(const int64_t* probes, int32_t* out, int64_t npairs, int k, uint64_t* parts) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const int64_t l = probes[i];
+    out[i] = (int32_t)l;
+    if (l < 0)
+        for (int j = 0; j < k; ++j) parts[(size_t)i * k + j] = 0ull;
 }
 
 // dst[n, ld] <- src[n, d], zero padding columns d..ld

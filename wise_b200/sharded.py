@@ -207,6 +207,11 @@ def train_ivf_sharded(index, x_local: torch.Tensor, niter: int = 10, seed: int =
     n_total = int(counts.sum().item())
     if n_total < k:
         raise RuntimeError(f"Number of training points ({n_total}) should be at least as large as number of clusters ({k})")
+    finite = torch.isfinite(x_local.sum(dtype=torch.float64)).to(torch.int32).view(1)  # NaN and +-Inf both poison a sum
+    if world > 1:
+        dist.all_reduce(finite, op=dist.ReduceOp.MIN, group=group)
+    if not int(finite.item()):
+        raise RuntimeError("input contains NaN's or Inf's")  # faiss Clustering::train [faiss-upstream]
     # initial centroids: k distinct global rows from a seeded permutation (same on every rank)
     # (drawn on the GPU: a CPU permutation of 10M indices costs more than a training iteration; same seed and same
     # generator on every rank, so all ranks pick the same rows)
