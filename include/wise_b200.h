@@ -188,6 +188,10 @@ int64_t wb_launch_count(const wb_index* h);
 /* Tensor-core path (batches of 5+ queries on large stores): epochs of the GEMM kernels launched so far, and how many
  * batches had to be repaired by the CUDA-core scan after a candidate-list overflow. */
 int wb_gemm_stats(const wb_index* h, int64_t* epochs, int64_t* fallbacks);
+/* IVF searches of up to 4 queries run as ONE cooperative launch: the coarse quantizer (faiss quantizer->search at the top
+ * of IndexIVF::search, reached from /root/reference/src/index/feature_search_index.py:113) is the prologue of the list
+ * scan.  Number of searches served that way so far (the others took the coarse scan + list scan launches). */
+int64_t wb_ivf_fused_searches(const wb_index* h);
 /* Device time (ms, CUDA events on the index's stream) of the scan kernel(s) of the last
  * wb_search / wb_search_dev call that finished; -1 if timing was off. */
 int wb_set_timing(wb_index* h, int on);

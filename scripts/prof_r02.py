@@ -1,5 +1,5 @@
 """Round-2 profiling targets: one mode per family of shipped kernels, small enough for `ncu --set full` replays.
-    python scripts/prof_r02.py flat1|flat16|flat1024|ivf_search|ivf_train|ivf_add [rows]
+    python scripts/prof_r02.py flat1|flat16|flat1024|ivf_search|ivf_train|ivf_add|ivf_fused [rows]
 Each mode prints its own CUDA-event timings, so the plain run doubles as a sanity check."""
 import ctypes as C, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -32,6 +32,24 @@ if mode.startswith("flat"):
     idx = faiss.IndexIDMap(faiss.IndexFlatIP(d)); bench.fill_index(idx, src, 0, rows)
     nq = int(mode[4:])
     search_dev(idx, bench.make_queries(src.centres, nq, d, 2025, dev), 100, reps=4 if nq == 1 else 2)
+elif mode == "ivf_fused":
+    # one-query IVF search as ONE cooperative launch (coarse quantizer inside the list scan, coarse.cuh): nlist 4096
+    # like BASELINE config 3; centroids = rows (no training), so every scan_topk_kernel launch here is a fused search
+    d, nlist = 512, 4096
+    src = bench.RowSource(rows, d, 50, dev)
+    ivf = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, nlist, faiss.METRIC_INNER_PRODUCT)
+    xs = torch.cat([x for _, _, x in src.chunks(0, nlist)])[:nlist]
+    ivf.set_centroids(np.ascontiguousarray(xs.cpu().numpy()))
+    ivf.reserve(rows)
+    for s, e, x in src.chunks(0, rows):
+        ids = torch.arange(s, e, dtype=torch.int64, device=dev)
+        _capi.check(L.wb_add_with_ids_dev(ivf._h, e - s, x.data_ptr(), ids.data_ptr(), st))
+    torch.cuda.synchronize()
+    q = bench.make_queries(src.centres, 1, d, 51, dev)
+    for nprobe in (8, 32):
+        f0 = L.wb_ivf_fused_searches(ivf._h)
+        search_dev(ivf, q, 100, nprobe=nprobe, reps=4)
+        print(f"ivf_fused: nprobe={nprobe}: {L.wb_ivf_fused_searches(ivf._h) - f0} of 4 searches were one launch", flush=True)
 else:
     d, nlist = 512, 1024
     src = bench.RowSource(rows, d, 50, dev)

@@ -388,3 +388,53 @@ def test_ivf_nan_rows_are_stored_but_never_returned(faiss, nq):
     assert not fresh.is_trained
     fresh.train(xb[clean][:10000])
     assert fresh.is_trained
+
+
+@pytest.mark.parametrize("n,d,nlist,k", [(40000, 512, 300, 100), (30000, 64, 7, 10), (120000, 128, 20000, 100),
+                                          (20000, 768, 1024, 1000)])
+def test_ivf_fused_coarse_matches_two_launch_path(faiss, monkeypatch, n, d, nlist, k):
+    """Up to 4 queries: the coarse quantizer runs as the prologue of the list-scan kernel (coarse.cuh) - ONE cooperative
+    launch per search.  Same (D, I) bytes as the two-launch path (coarse scan + merge, then the list scan) and parity
+    with the oracle, for one and many probes, fewer lists than CTAs, more lists than one histogram pass separates,
+    a zero query (every coarse score ties: the LOWER list ids are probed) and a NaN query (no list is probed)."""
+    from wise_b200 import _capi
+    L = _capi.lib()
+    xb = O.clustered_unit(n, d, min(2 * nlist, 4000), 70)
+    cent = O.kmeans_init(xb, nlist)
+    ids = np.arange(n, dtype=np.int64) * 3 + 1
+    idx = _ivf(faiss, xb, ids, cent)
+    _, _, ga = idx._export(0, n, want_assign=True)
+    a = ga.astype(np.int64)
+    xq = O.clustered_unit(4, d, min(2 * nlist, 4000), 71)
+    idx.search(xq, 1)  # groups the rows by list (K8) - not part of the launch counts below
+    for nq in (1, 2, 3, 4):
+        for nprobe in sorted({1, 5, 32, 128, nlist} & set(range(1, nlist + 1))):
+            idx.nprobe = nprobe
+            monkeypatch.setenv("WB_IVF_FUSE_COARSE", "1")
+            f0, l0 = L.wb_ivf_fused_searches(idx._h), L.wb_launch_count(idx._h)
+            D, I = idx.search(xq[:nq], k)
+            assert L.wb_ivf_fused_searches(idx._h) - f0 == 1, "the fused path was not taken"
+            assert L.wb_launch_count(idx._h) - l0 == 1, "a fused search is one launch"
+            monkeypatch.setenv("WB_IVF_FUSE_COARSE", "0")
+            f0 = L.wb_ivf_fused_searches(idx._h)
+            D2, I2 = idx.search(xq[:nq], k)
+            assert L.wb_ivf_fused_searches(idx._h) == f0
+            assert np.array_equal(I, I2) and np.array_equal(D.view(np.uint32), D2.view(np.uint32)), (nq, nprobe)
+            if nprobe in (1, 32, nlist) and nq in (1, 4) and nlist <= 1024:
+                Dr, Ir = O.ivf_search(xb, ids, a, cent, xq[:nq], k, nprobe)
+                O.compare_topk(D, I, Dr, Ir)
+    # degenerate coarse scores
+    idx.nprobe = min(5, nlist)
+    for q in (np.zeros((1, d), np.float32), np.full((1, d), np.nan, np.float32)):
+        monkeypatch.setenv("WB_IVF_FUSE_COARSE", "1")
+        D, I = idx.search(q, k)
+        monkeypatch.setenv("WB_IVF_FUSE_COARSE", "0")
+        D2, I2 = idx.search(q, k)
+        assert np.array_equal(I, I2) and np.array_equal(D.view(np.uint32), D2.view(np.uint32))
+    monkeypatch.setenv("WB_IVF_FUSE_COARSE", "1")
+    D, I = idx.search(np.zeros((1, d), np.float32), k)
+    in_first = np.isin(a, np.arange(idx.nprobe))  # rows of the lists 0 .. nprobe-1, lowest insertion positions first
+    want = ids[np.nonzero(in_first)[0][:k]]
+    assert np.array_equal(I[0, :want.size], want) and (I[0, want.size:] == -1).all()
+    D, I = idx.search(np.full((1, d), np.nan, np.float32), k)
+    assert (I == -1).all()

@@ -71,6 +71,7 @@ SIGNATURES = {
     "wb_tf32_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "wb_storage": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "wb_launch_count": (C.c_int64, [_vp]),
+    "wb_ivf_fused_searches": (C.c_int64, [_vp]),
     "wb_gemm_stats": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "wb_set_timing": (C.c_int, [_vp, C.c_int]),
     "wb_last_scan_ms": (C.c_float, [_vp]),

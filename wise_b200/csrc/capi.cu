@@ -131,6 +131,9 @@ struct wb_index {
     cudaEvent_t add_ev[kAddSlots] = {};
     bool add_pending[kAddSlots] = {};
     int64_t gemm_launches = 0, gemm_fallbacks = 0;
+    DevBuf ckeys;               // fused coarse quantizer: ordered centroid scores of the queries of one launch
+    bool coop_ok = false;       // the device takes cooperative launches (fused coarse quantizer, coarse.cuh)
+    int64_t coarse_fused = 0;   // IVF searches served by ONE launch (coarse quantizer inside the list scan)
     // device properties
     int sm_count = 148;
     int smem_max = 0;
@@ -170,6 +173,7 @@ static int create_common(int d, int device, bool ivf, int64_t nlist, wb_index** 
     h->trained = !ivf;
     h->sm_count = prop.multiProcessorCount;
     h->smem_max = (int)prop.sharedMemPerBlockOptin;
+    h->coop_ok = prop.cooperativeLaunch != 0;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (int i = 0; i < wb_index::kEvRing; ++i) {
         CK(cudaEventCreate(&h->ev0[i]));
@@ -208,7 +212,7 @@ extern "C" int wb_free(wb_index* h) {
     cudaFree(h->list_off);
     for (DevBuf* b : {&h->parts, &h->qbuf, &h->dbuf, &h->ibuf, &h->pD, &h->pI, &h->xbuf, &h->idbuf, &h->misc,
                       &h->kperm, &h->koff, &h->gimg, &h->gimg2, &h->gkeys, &h->gstate, &h->gmargin, &h->eD, &h->eI, &h->tailcnt, &h->ccnt, &h->ctot, &h->lmA, &h->lmB, &h->lmC,
-                      &h->lmD, &h->lmE, &h->lmF, &h->lmG})
+                      &h->lmD, &h->lmE, &h->lmF, &h->lmG, &h->ckeys})
         b->release();
     h->pin_q.release();
     h->pin_o.release();
@@ -229,6 +233,7 @@ extern "C" int wb_is_trained(const wb_index* h) { return h && h->trained; }
 extern "C" int64_t wb_nlist(const wb_index* h) { return h ? h->nlist : -1; }
 extern "C" int wb_is_ivf(const wb_index* h) { return h && h->ivf; }
 extern "C" int64_t wb_launch_count(const wb_index* h) { return h ? h->launches : -1; }
+extern "C" int64_t wb_ivf_fused_searches(const wb_index* h) { return h ? h->coarse_fused : -1; }
 extern "C" int wb_gemm_stats(const wb_index* h, int64_t* epochs, int64_t* fallbacks) {
     if (!h) return fail("NULL index");
     if (epochs) *epochs = h->gemm_launches;
@@ -389,6 +394,43 @@ static int launch_scan_rw(int RW, const ScanParams& p, dim3 grid, size_t smem, c
     return fail("bad RW %d", RW);
 }
 
+// Cooperative launch of the gather kernel (fused coarse quantizer: the CTAs of a query group meet at a barrier, so all
+// of them must be resident - the cooperative launch guarantees it or fails).
+template <int RW>
+static cudaError_t launch_scan_coop_t(const ScanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    static thread_local bool attr_done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 64 || !attr_done[dev]) {
+        e = cudaFuncSetAttribute(scan_topk_kernel<1, RW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        if (dev < 64) attr_done[dev] = true;
+    }
+    void* args[] = {const_cast<ScanParams*>(&p)};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(scan_topk_kernel<1, RW, true>), grid,
+                                       dim3(kScanThreads), args, smem, st);
+}
+
+static void apply_scan_cfg(const ScanCfg& c, ScanParams& p) {
+    p.P = c.P;
+    p.ck = c.ck;
+    p.nchunks = c.nchunks;
+    p.stages = c.stages;
+    p.single_copy = c.single_copy;
+    p.rw = c.RW;
+    p.prefetch_idx = env_int("WB_GATHER_PREFETCH", 1);
+}
+
+static cudaError_t launch_scan_coop(const ScanCfg& c, ScanParams& p, dim3 grid, cudaStream_t st) {
+    apply_scan_cfg(c, p);
+    switch (c.RW) {
+        case 4: return launch_scan_coop_t<4>(p, grid, c.smem, st);
+        case 2: return launch_scan_coop_t<2>(p, grid, c.smem, st);
+        default: return launch_scan_coop_t<1>(p, grid, c.smem, st);
+    }
+}
+
 static int launch_scan(const ScanCfg& c, bool gather, ScanParams& p, dim3 grid, cudaStream_t st) {
     p.P = c.P;
     p.ck = c.ck;
@@ -449,8 +491,9 @@ static int launch_merge_keys(wb_index* h, int64_t nq, int k, int64_t nparts, con
 constexpr int64_t kMaxGridY = 32768;
 static int ensure_tail_counters(wb_index* h, cudaStream_t st) {
     if (h->tailcnt.p) return 0;
-    TRY(h->tailcnt.ensure((size_t)2 * kMaxGridY * sizeof(unsigned int)));  // [arrivals | row-group dispensers]
-    CK(cudaMemsetAsync(h->tailcnt.p, 0, (size_t)2 * kMaxGridY * sizeof(unsigned int), st));
+    // [arrivals | row-group dispensers | coarse-barrier arrivals]
+    TRY(h->tailcnt.ensure((size_t)3 * kMaxGridY * sizeof(unsigned int)));
+    CK(cudaMemsetAsync(h->tailcnt.p, 0, (size_t)3 * kMaxGridY * sizeof(unsigned int), st));
     return 0;
 }
 
@@ -1332,50 +1375,9 @@ static int run_ivf_listmajor(wb_index* h, int64_t nq, const float* q_ld, int k, 
     return 0;
 }
 
-// ---- search --------------------------------------------------------------------------------
-static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld] */, int64_t k, int64_t nprobe, float* D,
-                           int64_t* I, cudaStream_t st, const ExchParams* ex = nullptr, bool* exchanged = nullptr) {
-    if (exchanged) *exchanged = false;
-    if (!h->ivf) return run_flat_any(h, h->rows, h->n, q_ld, nq, (int)k, h->ids, D, I, st, true, ex, exchanged);
-    if (!h->trained) return fail("IndexIVFFlat is not trained");
-    int np = (int)std::min<int64_t>(std::max<int64_t>(nprobe, 1), std::min<int64_t>(h->nlist, WB_MAX_K));
-    // K4: coarse quantizer = exhaustive scan of the centroids, top-nprobe
-    TRY(h->pD.ensure((size_t)nq * np * sizeof(float)));
-    TRY(h->pI.ensure((size_t)nq * np * sizeof(int64_t)));
-    TRY(run_flat_any(h, h->centroids, h->nlist, q_ld, nq, np, nullptr, h->pD.as<float>(), h->pI.as<int64_t>(), st, false));
-    if (h->csr_dirty) {
-        if (st != h->stream) CK(cudaStreamSynchronize(st));
-        TRY(ensure_csr(h));
-    }
-    // K5, batches: list-major - the probe table is inverted on the device and every probed list is streamed once per
-    // group of 8 of the queries that probe it (ivf_lm.cuh)
-    {
-        bool done = false;
-        TRY(run_ivf_listmajor(h, nq, q_ld, (int)k, np, D, I, st, &done));
-        if (done) return 0;
-    }
-    // K5: gather-scan of the probed lists
-    ScanCfg c;
-    TRY(plan_scan(h, 1, (int)k, true, np, &c));
-    int64_t S = nq >= h->sm_count ? 1 : std::max<int64_t>(1, (int64_t)h->sm_count / nq);
-    TRY(h->parts.ensure((size_t)nq * S * k * sizeof(uint64_t)));
-    ScanParams p{};
-    p.rows = h->rows;
-    p.nrows = 0;
-    p.ld = h->ld;
-    p.k = (int)k;
-    p.nparts = (int)S;
-    p.perm = h->slot_row;
-    p.row_pos = h->row_pos;
-    p.list_off = h->list_off;
-    p.nprobe = np;
-    if (ex && (nq > kMaxGridY || !env_int("WB_FUSE_EXCH", 1))) ex = nullptr;
-    int S_merge = 0;
-    const bool fuse = tail_fusable(c, (int)k, S, ex ? ex->world : 1, &S_merge);
-    if (fuse) {
-        TRY(ensure_tail_counters(h, st));
-        set_tail(p, h, c, S_merge, h->ids, ex ? ex->D : D, ex ? ex->I : I, (int)k, ex);
-    }
+// The query-major list scan: one launch per <= 32768 queries (the probe table is in h->pI), tail merge fused or not.
+static int run_gather_scan(wb_index* h, const ScanCfg& c, ScanParams& p, int64_t S, bool fuse, int64_t nq, const float* q_ld,
+                           int k, int np, float* D, int64_t* I, cudaStream_t st, const ExchParams* ex, bool* exchanged) {
     const int evs = (int)(h->ev_count % wb_index::kEvRing);
     if (h->timing) CK(cudaEventRecord(h->ev0[evs], st));
     for (int64_t q0 = 0; q0 < nq; q0 += kMaxGridY) {
@@ -1400,6 +1402,89 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
         return 0;
     }
     return launch_merge_keys(h, nq, (int)k, S, h->parts.as<uint64_t>(), h->ids, D, I, st);
+}
+
+// ---- search --------------------------------------------------------------------------------
+static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld] */, int64_t k, int64_t nprobe, float* D,
+                           int64_t* I, cudaStream_t st, const ExchParams* ex = nullptr, bool* exchanged = nullptr) {
+    if (exchanged) *exchanged = false;
+    if (!h->ivf) return run_flat_any(h, h->rows, h->n, q_ld, nq, (int)k, h->ids, D, I, st, true, ex, exchanged);
+    if (!h->trained) return fail("IndexIVFFlat is not trained");
+    int np = (int)std::min<int64_t>(std::max<int64_t>(nprobe, 1), std::min<int64_t>(h->nlist, WB_MAX_K));
+    if (h->csr_dirty) {
+        if (st != h->stream) CK(cudaStreamSynchronize(st));
+        TRY(ensure_csr(h));
+    }
+    // K5 plan: gather-scan of the probed lists, S CTAs per query
+    ScanCfg c;
+    TRY(plan_scan(h, 1, (int)k, true, np, &c));
+    int64_t S = nq >= h->sm_count ? 1 : std::max<int64_t>(1, (int64_t)h->sm_count / nq);
+    if (ex && (nq > kMaxGridY || !env_int("WB_FUSE_EXCH", 1))) ex = nullptr;
+    int S_merge = 0;
+    const bool fuse = tail_fusable(c, (int)k, S, ex ? ex->world : 1, &S_merge);
+    // K4 + K5 in one launch (coarse.cuh): a few queries, every CTA resident, the selection scratch fits the idle ring
+    const size_t ring_bytes = (size_t)c.stages * kConsumerWarps * c.RW * c.ck * 4;
+    bool fuse_coarse = fuse && h->coop_ok && nq <= env_int("WB_IVF_FUSE_COARSE_MAXQ", 4) && S * nq <= h->sm_count &&
+                       h->nlist < ((int64_t)1 << 30) && coarse_smem_layout(h->nlist, np).total <= ring_bytes &&
+                       env_int("WB_IVF_FUSE_COARSE", 1) && env_int("WB_IVF_LISTMAJOR", -1) != 1;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (!fuse_coarse) {
+            // K4: coarse quantizer = exhaustive scan of the centroids, top-nprobe
+            TRY(h->pD.ensure((size_t)nq * np * sizeof(float)));
+            TRY(h->pI.ensure((size_t)nq * np * sizeof(int64_t)));
+            TRY(run_flat_any(h, h->centroids, h->nlist, q_ld, nq, np, nullptr, h->pD.as<float>(), h->pI.as<int64_t>(), st, false));
+            // K5, batches: list-major - the probe table is inverted on the device and every probed list is streamed once
+            // per group of 8 of the queries that probe it (ivf_lm.cuh)
+            bool done = false;
+            TRY(run_ivf_listmajor(h, nq, q_ld, (int)k, np, D, I, st, &done));
+            if (done) return 0;
+        }
+        TRY(h->parts.ensure((size_t)nq * S * k * sizeof(uint64_t)));
+        ScanParams p{};
+        p.rows = h->rows;
+        p.nrows = 0;
+        p.ld = h->ld;
+        p.k = (int)k;
+        p.nparts = (int)S;
+        p.perm = h->slot_row;
+        p.row_pos = h->row_pos;
+        p.list_off = h->list_off;
+        p.nprobe = np;
+        if (fuse) {
+            TRY(ensure_tail_counters(h, st));
+            set_tail(p, h, c, S_merge, h->ids, ex ? ex->D : D, ex ? ex->I : I, (int)k, ex);
+        }
+        if (fuse_coarse) {
+            TRY(h->ckeys.ensure((size_t)nq * h->nlist * sizeof(uint32_t)));
+            p.centroids = h->centroids;
+            p.nlist = h->nlist;
+            p.coarse_keys = h->ckeys.as<uint32_t>();
+            p.coarse_count = h->tailcnt.as<unsigned int>() + 2 * kMaxGridY;
+            p.queries = q_ld;
+            p.nq = (int)nq;
+            p.parts = h->parts.as<uint64_t>();
+            const int evs = (int)(h->ev_count % wb_index::kEvRing);
+            if (h->timing) CK(cudaEventRecord(h->ev0[evs], st));
+            const cudaError_t e = launch_scan_coop(c, p, dim3((unsigned)S, (unsigned)nq), st);
+            if (e != cudaSuccess) {
+                // (a partitioned device can refuse a full-width cooperative grid: two launches from now on)
+                cudaGetLastError();
+                h->coop_ok = false;
+                fuse_coarse = false;
+                continue;
+            }
+            if (h->timing) {
+                CK(cudaEventRecord(h->ev1[evs], st));
+                h->ev_count++;
+            }
+            h->launches++;
+            h->coarse_fused++;
+            if (ex && exchanged) *exchanged = true;
+            return 0;
+        }
+        return run_gather_scan(h, c, p, S, fuse, nq, q_ld, (int)k, np, D, I, st, ex, exchanged);
+    }
+    return fail("unreachable");
 }
 
 static int check_search_args(const wb_index* h, int64_t nq, const void* q, int64_t k, const void* D, const void* I) {

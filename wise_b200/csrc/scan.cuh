@@ -20,6 +20,7 @@
 //     query at the end, merged by merge_topk_kernel (merge.cuh).
 // Algorithmic bytes per launch: nrows * ld * 4 (the row store is read exactly once per pass).
 #pragma once
+#include "coarse.cuh"
 #include "exchange.cuh"
 
 namespace wb {
@@ -52,8 +53,14 @@ struct ScanParams {
     const uint32_t* perm;     // CSR: row index per slot; null when the rows are physically grouped by list
     const uint32_t* row_pos;  // storage row -> insertion position (the tie rule and the id lookup); null: identity
     const int64_t* list_off;  // CSR: [nlist + 1]
-    const int64_t* probes;    // [nq][nprobe] list ids (-1 = none)
+    const int64_t* probes;    // [nq][nprobe] list ids (-1 = none); unused when the coarse quantizer is fused
     int nprobe;
+    // fused coarse quantizer (coarse.cuh; gather mode, cooperative launch, fuse_tail set): the CTAs of a query group
+    // score the centroid table, meet at coarse_count[blockIdx.y] and each select the top-nprobe lists themselves.
+    const float* centroids;      // [nlist][ld]; null: the probes come from `probes`
+    int64_t nlist;
+    uint32_t* coarse_keys;       // [gridDim.y][nlist] scratch: ordered scores
+    unsigned int* coarse_count;  // [gridDim.y] arrival counters, zero between launches (reset with tail_count)
     // fused tail (K3 inside K1/K5): the LAST CTA of a query group to finish merges the group's nparts lists and
     // emits (D, I) itself - a search is one launch instead of scan + merge.  With `exchange` set it also pushes the
     // merged rows to the peer GPUs' mailboxes, waits for theirs and emits the GLOBAL top-k (exchange.cuh).
@@ -185,6 +192,36 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     }
     int64_t total = p.nrows;
     GatherCtx G{prefix, pbase, p.perm, p.nprobe};
+    if constexpr (GATHER && NQ == 1) {
+        if (p.centroids) {
+            // ---- fused K4: top-nprobe of the centroid scores, identical in every CTA of the group (coarse.cuh) ----
+            const CoarseSmem CL = coarse_smem_layout(p.nlist, p.nprobe);
+            unsigned char* scratch = reinterpret_cast<unsigned char*>(ring);  // the ring is idle until the producer starts
+            uint32_t* ckeys = reinterpret_cast<uint32_t*>(scratch + CL.keys);
+            uint64_t* sel = reinterpret_cast<uint64_t*>(scratch + CL.sel);
+            const int nl = (int)p.nlist;
+            __syncthreads();  // the query is in shared memory
+            const int64_t per = (p.nlist + gridDim.x - 1) / gridDim.x;
+            const int64_t c0 = (int64_t)blockIdx.x * per;
+            uint32_t* gkeys = p.coarse_keys + (size_t)blockIdx.y * p.nlist;
+            coarse_score_slice<kScanThreads>(p.centroids, ld, reinterpret_cast<const float4*>(qs), c0,
+                                             min(p.nlist, c0 + per), gkeys, tid);
+            group_arrive_wait(&p.coarse_count[blockIdx.y], gridDim.x);
+            for (int i = tid; i < nl; i += kScanThreads) ckeys[i] = __ldcg(gkeys + i);
+            const int Pn = pow2_ceil(p.nprobe);
+            for (int i = p.nprobe + tid; i < Pn; i += kScanThreads) sel[i] = 0ull;
+            __syncthreads();
+            block_select_top_keys<kScanThreads>(ckeys, nl, p.nprobe, reinterpret_cast<uint32_t*>(scratch + CL.hist),
+                                                reinterpret_cast<uint32_t*>(scratch + CL.chunk), scratch + CL.ctl, sel, tid);
+            bitonic_sort_desc<kScanThreads>(sel, Pn, 1, tid, -1);
+            for (int j = tid; j < p.nprobe; j += kScanThreads) {
+                const uint64_t key = sel[j];
+                pbase[j] = (key >> 32) ? (int64_t)key_pos(key) : (int64_t)-1;  // read back as the list id below
+            }
+            fence_proxy_async();  // generic-proxy writes to the ring precede the bulk copies that will land there
+            __syncthreads();
+        }
+    }
     if constexpr (GATHER) {
         if (warp == 0) {  // exclusive prefix sum of the probed list sizes
             uint32_t carry = 0;
@@ -192,7 +229,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                 const int j = base + lane;
                 uint32_t sz = 0;
                 if (j < p.nprobe) {
-                    const int64_t lid = p.probes[(size_t)blockIdx.y * p.nprobe + j];
+                    const int64_t lid = p.centroids ? pbase[j] : p.probes[(size_t)blockIdx.y * p.nprobe + j];
                     int64_t b = 0;
                     if (lid >= 0) {
                         b = p.list_off[lid];
@@ -388,6 +425,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             if (tail_last) {  // ready for the next launch on this stream (every CTA has drawn its last group by now)
                 p.tail_count[blockIdx.y] = 0;
                 if (p.group_count) p.group_count[blockIdx.y] = 0;
+                if (p.coarse_count) p.coarse_count[blockIdx.y] = 0;  // every CTA of the group left that barrier long ago
             }
         }
         named_bar_sync(kBarConsumers, kConsumerThreads);
