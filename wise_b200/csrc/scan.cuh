@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             __syncthreads();
             block_select_top_keys<kScanThreads>(ckeys, nl, p.nprobe, reinterpret_cast<uint32_t*>(scratch + CL.hist),
                                                 reinterpret_cast<uint32_t*>(scratch + CL.chunk), scratch + CL.ctl, sel, tid);
-            bitonic_sort_desc<kScanThreads>(sel, Pn, 1, tid, -1);
+            if (Pn >= 2) bitonic_sort_desc<kScanThreads>(sel, Pn, 1, tid, -1);
             for (int j = tid; j < p.nprobe; j += kScanThreads) {
                 const uint64_t key = sel[j];
                 pbase[j] = (key >> 32) ? (int64_t)key_pos(key) : (int64_t)-1;  // read back as the list id below
