@@ -10,33 +10,30 @@
 //   1. score a slice of the centroid table each (warp per 4 centroids, coalesced 128-bit loads, no staging - the table
 //      is L2 resident) and publish the ORDERED scores (order_f32) to a global array,
 //   2. meet at a group barrier (arrival counter; the launch is cooperative, so every CTA is resident),
-//   3. each select the SAME top-nprobe of the nlist scores - exact radix selection on (score, ~list id) keys by
-//      range-adaptive 1024-bin histograms (2-3 passes over keys held in shared memory), then a bitonic sort of the
-//      nprobe winners - and go on to scan the lists.
+//   3. each select the SAME top-nprobe of the nlist scores - exact radix selection on (score, ~list id) keys
+//      (radix_select.cuh: range-adaptive 1024-bin histograms, 2-3 passes over keys held in shared memory), then a
+//      bitonic sort of the nprobe winners - and go on to scan the lists.
 // The selection is redundant per CTA (148 x nlist keys from L2) but needs no second barrier and no broadcast.
 // Order of the winners: score descending, ties by LOWER list id - the order merge_topk_kernel gave the probe table.
 // A NaN score gets key 0 (never wins against a real score; a winner with key 0 becomes probe -1 = no list).
 #pragma once
-#include "common.cuh"
+#include "radix_select.cuh"
 
 namespace wb {
 
-constexpr int kSelBins = 1024;          // histogram bins of one selection pass (32 chunks of 32)
 constexpr int kCoarseRowsPerWarp = 4;   // centroids scored together by one warp (independent loads in flight)
 
 struct CoarseSmem {
-    size_t keys, hist, chunk, ctl, sel, total;
+    size_t keys, scratch, sel, total;
 };
 
 // Scratch of the coarse phase inside the (still idle) ring of the scan kernel.
 __host__ __device__ inline CoarseSmem coarse_smem_layout(int64_t nlist, int np) {
     CoarseSmem L;
     size_t o = 0;
-    L.keys = o;  o += ((size_t)nlist * 4 + 15) & ~(size_t)15;   // ordered scores of every centroid
-    L.hist = o;  o += (size_t)kSelBins * 4;
-    L.chunk = o; o += 32 * 4;                                   // per-chunk totals (and per-warp min / max)
-    L.ctl = o;   o += 64;                                       // lo, hi (u64) | sel_n, need, bstar, above, cnt (int)
-    L.sel = o;   o += (size_t)pow2_ceil(np) * 8;
+    L.keys = o;    o += ((size_t)nlist * 4 + 15) & ~(size_t)15;   // ordered scores of every centroid
+    L.scratch = o; o += kRadixScratchBytes;                       // block_radix_select
+    L.sel = o;     o += (size_t)pow2_ceil(np) * 8;
     L.total = o;
     return L;
 }
@@ -113,114 +110,6 @@ __device__ __forceinline__ void group_arrive_wait(unsigned int* counter, unsigne
         __threadfence();
     }
     __syncthreads();
-}
-
-// Exact top-`need` of the n keys coarse_key64(keys[i], i) (all distinct), written to sel[0 .. need) in arbitrary
-// order.  Range-adaptive radix selection: every pass histograms the keys of the current range [lo, hi] into <= 1024
-// equal-width bins, takes every bin above the one that holds the need-th largest key, and either finishes (that bin is
-// taken whole) or recurses into it.  The range shrinks by >= 2^10 per pass and a width-1 bin holds one key, so the loop
-// ends after at most 7 passes; 2-3 in practice (the first pass spans [min score, max score]).
-// Called by all NT threads; n >= need >= 1.
-template <int NT>
-__device__ __forceinline__ void block_select_top_keys(const uint32_t* keys, int n, int need0, uint32_t* hist,
-                                                      uint32_t* chunk, unsigned char* ctl_raw, uint64_t* sel, int tid) {
-    const int warp = tid >> 5, lane = tid & 31;
-    uint64_t* ctl64 = reinterpret_cast<uint64_t*>(ctl_raw);           // [0] lo, [1] hi
-    int* ctl = reinterpret_cast<int*>(ctl_raw + 16);                  // [0] sel_n [1] need [2] bstar [3] above [4] cnt
-    // ---- range of the score keys ---------------------------------------------------------------------------
-    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
-    for (int i = tid; i < n; i += NT) {
-        const uint32_t v = keys[i];
-        mn = min(mn, v);
-        mx = max(mx, v);
-    }
-    mn = __reduce_min_sync(0xffffffffu, mn);
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    if (lane == 0) {
-        chunk[warp] = mn;
-        chunk[16 + warp] = mx;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < NT / 32; ++w) {
-            mn = min(mn, chunk[w]);
-            mx = max(mx, chunk[16 + w]);
-        }
-        ctl64[0] = (uint64_t)mn << 32;
-        ctl64[1] = ((uint64_t)mx << 32) | 0xFFFFFFFFull;
-        ctl[0] = 0;
-        ctl[1] = need0;
-    }
-    __syncthreads();
-    for (int pass = 0; pass < 8; ++pass) {
-        const uint64_t lo = ctl64[0], hi = ctl64[1];
-        const int need = ctl[1];
-        const uint64_t range = hi - lo;
-        const int sh = range < (uint64_t)kSelBins ? 0 : (64 - __clzll((long long)range)) - 10;  // (range >> sh) < 1024
-        for (int i = tid; i < kSelBins; i += NT) hist[i] = 0u;
-        __syncthreads();
-        for (int i = tid; i < n; i += NT) {
-            const uint64_t kk = coarse_key64(keys[i], (uint32_t)i);
-            if (kk >= lo && kk <= hi) atomicAdd(&hist[(uint32_t)((kk - lo) >> sh)], 1u);
-        }
-        __syncthreads();
-        for (int c = warp; c < 32; c += NT / 32) {
-            const uint32_t s = __reduce_add_sync(0xffffffffu, hist[c * 32 + lane]);
-            if (lane == 0) chunk[c] = s;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            // suffix sums (inclusive) over the 32 chunk totals, then over the 32 bins of the boundary chunk
-            const uint32_t cv = chunk[lane];
-            uint32_t cs = cv;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_down_sync(0xffffffffu, cs, o);
-                if (lane + o < 32) cs += t;
-            }
-            const unsigned mc = __ballot_sync(0xffffffffu, cs >= (uint32_t)need);  // lane 0 always: the range holds >= need keys
-            const int cstar = 31 - __clz(mc);
-            const uint32_t above_chunks = __shfl_sync(0xffffffffu, cs, cstar) - __shfl_sync(0xffffffffu, cv, cstar);
-            const uint32_t hv = hist[cstar * 32 + lane];
-            uint32_t hs = hv;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_down_sync(0xffffffffu, hs, o);
-                if (lane + o < 32) hs += t;
-            }
-            hs += above_chunks;  // keys in bins >= cstar * 32 + lane
-            const unsigned mb = __ballot_sync(0xffffffffu, hs >= (uint32_t)need);
-            const int bl = 31 - __clz(mb);
-            const uint32_t ge = __shfl_sync(0xffffffffu, hs, bl), cnt = __shfl_sync(0xffffffffu, hv, bl);
-            if (lane == 0) {
-                ctl[2] = cstar * 32 + bl;
-                ctl[3] = (int)(ge - cnt);
-                ctl[4] = (int)cnt;
-            }
-        }
-        __syncthreads();
-        const uint32_t bstar = (uint32_t)ctl[2];
-        const int above = ctl[3], cnt = ctl[4];
-        const bool last = cnt == need - above;  // the boundary bin is taken whole: done
-        for (int i = tid; i < n; i += NT) {
-            const uint64_t kk = coarse_key64(keys[i], (uint32_t)i);
-            if (kk >= lo && kk <= hi) {
-                const uint32_t b = (uint32_t)((kk - lo) >> sh);
-                if (b > bstar || (last && b == bstar)) sel[atomicAdd(&ctl[0], 1)] = kk;
-            }
-        }
-        __syncthreads();
-        if (last) break;
-        if (tid == 0) {
-            const uint64_t nlo = lo + ((uint64_t)bstar << sh);
-            uint64_t nhi = nlo + (((uint64_t)1 << sh) - 1);
-            if (nhi > hi) nhi = hi;
-            ctl64[0] = nlo;
-            ctl64[1] = nhi;
-            ctl[1] = need - above;
-        }
-        __syncthreads();
-    }
 }
 
 }  // namespace wb

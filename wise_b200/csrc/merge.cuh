@@ -6,6 +6,7 @@
 #pragma once
 #include <float.h>
 #include "common.cuh"
+#include "radix_select.cuh"
 
 namespace wb {
 

@@ -1,0 +1,185 @@
+// radix_select.cuh - exact block-level top-k of n DISTINCT 64-bit keys (0 = empty slot) without sorting them.
+//
+// Used where a thread block must pick k winners out of many more candidates and only the winners need an order:
+//   * the merge of the per-CTA top-k lists at the tail of a scan (K3 inside K1 / K5: 148 x k keys -> k), and the
+//     merge of the per-rank rows after the NVLink exchange - faiss's result-handler merge / heap_reorder
+//     [faiss-upstream], reached from /root/reference/src/index/feature_search_index.py:113;
+//   * the top-nprobe of the centroid scores in the fused coarse quantizer (coarse.cuh).
+// A bitonic sort of the 1024-key merge buffer cost the LAST CTA of every scan ~20 us (ncu: the SM that merges is
+// active for 107k cycles of a launch whose other SMs finish after 57k); selection needs 2-3 cheap passes instead:
+// every pass histograms the keys of the current range [lo, hi] into <= 1024 equal-width bins, takes every bin above the
+// one that holds the need-th largest key, and either finishes (that bin is taken whole) or recurses into it.  The first
+// range is [min key, max key], so the bins resolve the score distribution at once; a range shrinks by >= 2^10 per pass
+// and a width-1 bin holds one key, so the loop ends after at most 7 passes.  The k winners are then bitonic-sorted
+// (128 keys for k = 100) by the caller.  tests/test_coarse_model.py checks the arithmetic on the CPU.
+#pragma once
+#include "common.cuh"
+
+namespace wb {
+
+constexpr int kSelBins = 1024;  // histogram bins of one selection pass (32 chunks of 32)
+
+// Shared-memory scratch of one selection (the caller places it; 16-byte aligned).
+constexpr size_t kRadixScratchBytes = (size_t)kSelBins * 4 + 32 * 4 + 1024;
+struct RadixScratch {
+    uint32_t* hist;      // [kSelBins]
+    uint32_t* chunk;     // [32] per-chunk totals
+    unsigned char* ctl;  // [1024]: lo, hi (u64) | sel_n, need, bstar, above, cnt (int) | per-warp min / max / count
+    __device__ __forceinline__ explicit RadixScratch(unsigned char* base)
+        : hist(reinterpret_cast<uint32_t*>(base)), chunk(reinterpret_cast<uint32_t*>(base) + kSelBins),
+          ctl(base + (size_t)kSelBins * 4 + 32 * 4) {}
+};
+
+template <int NT>
+__device__ __forceinline__ void rs_sync(int bar_id) {
+    if (bar_id < 0) __syncthreads();
+    else named_bar_sync(bar_id, NT);
+}
+
+// Top-min(need0, #non-empty) of the keys key_at(i), i in [0, n), written to sel[] in arbitrary order; returns how many.
+// Non-empty keys must be distinct.  Runs on NT threads (whole warps, tid in [0, NT)) that share barrier bar_id
+// (< 0: the whole CTA); key_at must be cheap and side-effect free (it is evaluated in every pass).
+template <int NT, class KeyAt>
+__device__ __forceinline__ int block_radix_select(int n, int need0, KeyAt key_at, RadixScratch sc, uint64_t* sel, int tid,
+                                                  int bar_id) {
+    static_assert(NT % 32 == 0 && NT <= 1024, "whole warps");
+    const int warp = tid >> 5, lane = tid & 31;
+    uint32_t* hist = sc.hist;
+    uint32_t* chunk = sc.chunk;
+    uint64_t* ctl64 = reinterpret_cast<uint64_t*>(sc.ctl);            // [0] lo, [1] hi
+    int* ctl = reinterpret_cast<int*>(sc.ctl + 16);                   // [0] sel_n [1] need [2] bstar [3] above [4] cnt
+    uint64_t* wmin = reinterpret_cast<uint64_t*>(sc.ctl + 64);        // [32]
+    uint64_t* wmax = wmin + 32;                                       // [32]
+    uint32_t* wcnt = reinterpret_cast<uint32_t*>(sc.ctl + 64 + 512);  // [32]
+    // ---- range and number of the non-empty keys -------------------------------------------------------------
+    uint64_t mn = ~0ull, mx = 0ull;
+    uint32_t nz = 0;
+    for (int i = tid; i < n; i += NT) {
+        const uint64_t v = key_at(i);
+        if (v) {
+            mn = v < mn ? v : mn;
+            mx = v > mx ? v : mx;
+            ++nz;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint64_t a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    nz = __reduce_add_sync(0xffffffffu, nz);
+    if (lane == 0) {
+        wmin[warp] = mn;
+        wmax[warp] = mx;
+        wcnt[warp] = nz;
+    }
+    rs_sync<NT>(bar_id);
+    if (tid == 0) {
+        for (int w = 1; w < NT / 32; ++w) {
+            mn = wmin[w] < mn ? wmin[w] : mn;
+            mx = wmax[w] > mx ? wmax[w] : mx;
+            nz += wcnt[w];
+        }
+        ctl64[0] = mn;
+        ctl64[1] = mx;
+        ctl[0] = 0;
+        ctl[1] = min(need0, (int)nz);
+    }
+    rs_sync<NT>(bar_id);
+    const int need_total = ctl[1];
+    if (need_total <= 0) return 0;  // (uniform)
+    for (int pass = 0; pass < 8; ++pass) {
+        const uint64_t lo = ctl64[0], hi = ctl64[1];
+        const int need = ctl[1];
+        const uint64_t range = hi - lo;
+        const int sh = range < (uint64_t)kSelBins ? 0 : (64 - __clzll((long long)range)) - 10;  // (range >> sh) < 1024
+        for (int i = tid; i < kSelBins; i += NT) hist[i] = 0u;
+        rs_sync<NT>(bar_id);
+        for (int i = tid; i < n; i += NT) {
+            const uint64_t kk = key_at(i);
+            if (kk >= lo && kk <= hi) atomicAdd(&hist[(uint32_t)((kk - lo) >> sh)], 1u);  // lo > 0: empty keys never count
+        }
+        rs_sync<NT>(bar_id);
+        for (int c = warp; c < 32; c += NT / 32) {
+            const uint32_t s = __reduce_add_sync(0xffffffffu, hist[c * 32 + lane]);
+            if (lane == 0) chunk[c] = s;
+        }
+        rs_sync<NT>(bar_id);
+        if (warp == 0) {
+            // suffix sums (inclusive) over the 32 chunk totals, then over the 32 bins of the boundary chunk
+            const uint32_t cv = chunk[lane];
+            uint32_t cs = cv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_down_sync(0xffffffffu, cs, o);
+                if (lane + o < 32) cs += t;
+            }
+            const unsigned mc = __ballot_sync(0xffffffffu, cs >= (uint32_t)need);  // lane 0 always: the range holds >= need keys
+            const int cstar = 31 - __clz(mc);
+            const uint32_t above_chunks = __shfl_sync(0xffffffffu, cs, cstar) - __shfl_sync(0xffffffffu, cv, cstar);
+            const uint32_t hv = hist[cstar * 32 + lane];
+            uint32_t hs = hv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_down_sync(0xffffffffu, hs, o);
+                if (lane + o < 32) hs += t;
+            }
+            hs += above_chunks;  // keys in bins >= cstar * 32 + lane
+            const unsigned mb = __ballot_sync(0xffffffffu, hs >= (uint32_t)need);
+            const int bl = 31 - __clz(mb);
+            const uint32_t ge = __shfl_sync(0xffffffffu, hs, bl), cnt = __shfl_sync(0xffffffffu, hv, bl);
+            if (lane == 0) {
+                ctl[2] = cstar * 32 + bl;
+                ctl[3] = (int)(ge - cnt);
+                ctl[4] = (int)cnt;
+            }
+        }
+        rs_sync<NT>(bar_id);
+        const uint32_t bstar = (uint32_t)ctl[2];
+        const int above = ctl[3], cnt = ctl[4];
+        const bool last = cnt == need - above;  // the boundary bin is taken whole: done
+        for (int i = tid; i < n; i += NT) {
+            const uint64_t kk = key_at(i);
+            if (kk >= lo && kk <= hi) {
+                const uint32_t b = (uint32_t)((kk - lo) >> sh);
+                if (b > bstar || (last && b == bstar)) sel[atomicAdd(&ctl[0], 1)] = kk;
+            }
+        }
+        rs_sync<NT>(bar_id);
+        if (last) break;
+        if (tid == 0) {
+            const uint64_t nlo = lo + ((uint64_t)bstar << sh);
+            uint64_t nhi = nlo + (((uint64_t)1 << sh) - 1);
+            if (nhi > hi) nhi = hi;
+            ctl64[0] = nlo;
+            ctl64[1] = nhi;
+            ctl[1] = need - above;
+        }
+        rs_sync<NT>(bar_id);
+    }
+    return need_total;
+}
+
+// Shared-memory region of a key merge: keys[M] | best[pow2_ceil(k)] | selection scratch.
+__host__ __device__ inline size_t radix_merge_bytes(int64_t M, int k) {
+    return (((size_t)M + (size_t)pow2_ceil(k)) * 8 + kRadixScratchBytes + 15) & ~(size_t)15;
+}
+
+// Top-k of the M keys load(i) (0 = empty): stages them in `region` (radix_merge_bytes(M, k) bytes of shared memory),
+// selects, sorts the winners.  Returns the pow2_ceil(k) sorted (descending, zero-padded) best keys, inside `region`.
+template <int NT, class Load>
+__device__ __forceinline__ uint64_t* block_topk_radix(unsigned char* region, int M, int k, Load load, int tid, int bar_id) {
+    uint64_t* keys = reinterpret_cast<uint64_t*>(region);
+    const int Pk = pow2_ceil(k);
+    uint64_t* best = keys + M;
+    for (int i = tid; i < M; i += NT) keys[i] = load(i);
+    for (int i = tid; i < Pk; i += NT) best[i] = 0ull;
+    rs_sync<NT>(bar_id);
+    block_radix_select<NT>(M, k, [&](int i) { return keys[i]; }, RadixScratch(reinterpret_cast<unsigned char*>(best + Pk)),
+                           best, tid, bar_id);
+    if (Pk >= 2) bitonic_sort_desc<NT>(best, Pk, 1, tid, bar_id);
+    return best;
+}
+
+}  // namespace wb

@@ -66,6 +66,7 @@ struct ScanParams {
     // merged rows to the peer GPUs' mailboxes, waits for theirs and emits the GLOBAL top-k (exchange.cuh).
     int fuse_tail;
     int S_merge;              // sort-buffer entries of the fused merge (the idle ring holds them)
+    int radix_bytes;          // > 0: the fused merge selects by radix (radix_select.cuh) in this many bytes of the ring
     unsigned int* tail_count; // [gridDim.y] arrival counters, zero between launches (the last CTA resets its own)
     // dynamic row-group scheduling (fused-tail launches with whole-row stages): CTAs draw the next row group from
     // group_count[blockIdx.y] instead of striding by gridDim.x.  SMs stream at slightly different rates (ncu: the
@@ -211,8 +212,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             const int Pn = pow2_ceil(p.nprobe);
             for (int i = p.nprobe + tid; i < Pn; i += kScanThreads) sel[i] = 0ull;
             __syncthreads();
-            block_select_top_keys<kScanThreads>(ckeys, nl, p.nprobe, reinterpret_cast<uint32_t*>(scratch + CL.hist),
-                                                reinterpret_cast<uint32_t*>(scratch + CL.chunk), scratch + CL.ctl, sel, tid);
+            block_radix_select<kScanThreads>(nl, p.nprobe, [&](int i) { return coarse_key64(ckeys[i], (uint32_t)i); },
+                                             RadixScratch(scratch + CL.scratch), sel, tid, -1);
             if (Pn >= 2) bitonic_sort_desc<kScanThreads>(sel, Pn, 1, tid, -1);
             for (int j = tid; j < p.nprobe; j += kScanThreads) {
                 const uint64_t key = sel[j];
@@ -436,15 +437,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             const int64_t q = q0 + l;
             const uint64_t* src = p.parts + (size_t)q * p.nparts * k;
             const int64_t M = (int64_t)p.nparts * k;
-            if (!block_select_topk_lists<kConsumerThreads>(
-                    buf, p.S_merge, k, p.nparts, [&](int li, int r) { return __ldcg(src + (size_t)li * k + r); }, &tail_cnt,
-                    ctid, kBarConsumers)) {
+            const uint64_t* best = buf;
+            if (p.radix_bytes) {
+                // no sort of the candidates: 2-3 histogram passes pick the k winners, only those are sorted
+                best = block_topk_radix<kConsumerThreads>(reinterpret_cast<unsigned char*>(ring), (int)M, k,
+                                                          [&](int i) { return __ldcg(src + i); }, ctid, kBarConsumers);
+            } else if (!block_select_topk_lists<kConsumerThreads>(
+                           buf, p.S_merge, k, p.nparts, [&](int li, int r) { return __ldcg(src + (size_t)li * k + r); },
+                           &tail_cnt, ctid, kBarConsumers)) {
                 named_bar_sync(kBarConsumers, kConsumerThreads);
                 block_select_topk<kConsumerThreads>(buf, p.S_merge, k, M, [&](int64_t c) { return __ldcg(src + c); },
                                                     &tail_cnt, ctid, kBarConsumers);
             }
             auto local = [&](int j, float& d, int64_t& id) {
-                const uint64_t key = buf[j];
+                const uint64_t key = best[j];
                 d = -FLT_MAX;
                 id = -1;
                 if (key) {
@@ -464,7 +470,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                 named_bar_sync(kBarConsumers, kConsumerThreads);  // buf is reused by the next query
             } else {
                 // the local winners move to the second half of the buffer region: the exchange merge sorts in `buf`
-                float* ld_s = reinterpret_cast<float*>(buf + p.S_merge);
+                float* ld_s = p.radix_bytes ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ring) + p.radix_bytes)
+                                            : reinterpret_cast<float*>(buf + p.S_merge);
                 int64_t* li_s = reinterpret_cast<int64_t*>(ld_s + ((k + 1) & ~1));
                 for (int j = ctid; j < k; j += kConsumerThreads) local(j, ld_s[j], li_s[j]);
                 named_bar_sync(kBarConsumers, kConsumerThreads);
