@@ -192,6 +192,10 @@ int wb_gemm_stats(const wb_index* h, int64_t* epochs, int64_t* fallbacks);
  * of IndexIVF::search, reached from /root/reference/src/index/feature_search_index.py:113) is the prologue of the list
  * scan.  Number of searches served that way so far (the others took the coarse scan + list scan launches). */
 int64_t wb_ivf_fused_searches(const wb_index* h);
+/* Diagnostics (replaces nothing in the reference): with WB_PHASE_TS=1 in the environment the scan kernel's CTAs stamp
+ * %globaltimer at their phase boundaries (scan.cuh ScanParams::phase_ts lists the 10 phases); this copies the stamps of
+ * the first `ctas` CTAs of the last scan-served search, 16 uint64 per CTA (scripts/phase_times.py prints them). */
+int wb_phase_stamps(wb_index* h, uint64_t* out_host, int ctas);
 /* Device time (ms, CUDA events on the index's stream) of the scan kernel(s) of the last
  * wb_search / wb_search_dev call that finished; -1 if timing was off. */
 int wb_set_timing(wb_index* h, int on);

@@ -131,6 +131,7 @@ struct wb_index {
     cudaEvent_t add_ev[kAddSlots] = {};
     bool add_pending[kAddSlots] = {};
     int64_t gemm_launches = 0, gemm_fallbacks = 0;
+    DevBuf phase;               // WB_PHASE_TS=1: per-CTA phase stamps of the last fused-tail scan launch (diagnostics)
     DevBuf ckeys;               // fused coarse quantizer: ordered centroid scores of the queries of one launch
     bool coop_ok = false;       // the device takes cooperative launches (fused coarse quantizer, coarse.cuh)
     int64_t coarse_fused = 0;   // IVF searches served by ONE launch (coarse quantizer inside the list scan)
@@ -212,7 +213,7 @@ extern "C" int wb_free(wb_index* h) {
     cudaFree(h->list_off);
     for (DevBuf* b : {&h->parts, &h->qbuf, &h->dbuf, &h->ibuf, &h->pD, &h->pI, &h->xbuf, &h->idbuf, &h->misc,
                       &h->kperm, &h->koff, &h->gimg, &h->gimg2, &h->gkeys, &h->gstate, &h->gmargin, &h->eD, &h->eI, &h->tailcnt, &h->ccnt, &h->ctot, &h->lmA, &h->lmB, &h->lmC,
-                      &h->lmD, &h->lmE, &h->lmF, &h->lmG, &h->ckeys})
+                      &h->lmD, &h->lmE, &h->lmF, &h->lmG, &h->ckeys, &h->phase})
         b->release();
     h->pin_q.release();
     h->pin_o.release();
@@ -234,6 +235,16 @@ extern "C" int64_t wb_nlist(const wb_index* h) { return h ? h->nlist : -1; }
 extern "C" int wb_is_ivf(const wb_index* h) { return h && h->ivf; }
 extern "C" int64_t wb_launch_count(const wb_index* h) { return h ? h->launches : -1; }
 extern "C" int64_t wb_ivf_fused_searches(const wb_index* h) { return h ? h->coarse_fused : -1; }
+constexpr size_t kPhaseCtas = 1024;  // phase stamps: CTAs of query group 0 (the kernel ignores blockIdx.x >= 1024)
+extern "C" int wb_phase_stamps(wb_index* h, uint64_t* out_host, int ctas) {
+    if (!h || !out_host) return fail("NULL argument");
+    if (!h->phase.p) return fail("no phase stamps: set WB_PHASE_TS=1 before the search");
+    if (ctas < 1 || (size_t)ctas > kPhaseCtas) return fail("ctas out of range");
+    TRY(set_dev(h));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out_host, h->phase.p, (size_t)ctas * 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
 extern "C" int wb_gemm_stats(const wb_index* h, int64_t* epochs, int64_t* fallbacks) {
     if (!h) return fail("NULL index");
     if (epochs) *epochs = h->gemm_launches;
@@ -522,6 +533,9 @@ static void set_tail(ScanParams& p, wb_index* h, const ScanCfg& c, int S_merge, 
     p.fuse_tail = 1;
     p.S_merge = S_merge;
     p.radix_bytes = radix_bytes;
+    p.phase_ts = nullptr;
+    if (env_int("WB_PHASE_TS", 0) && h->phase.ensure(kPhaseCtas * 16 * sizeof(unsigned long long)) == 0)
+        p.phase_ts = h->phase.as<unsigned long long>();
     p.tail_count = h->tailcnt.as<unsigned int>();
     p.group_count = (c.nchunks == 1 && env_int("WB_SCAN_DYNAMIC", 1)) ? h->tailcnt.as<unsigned int>() + kMaxGridY : nullptr;
     p.ids = ids;

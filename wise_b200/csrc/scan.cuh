@@ -77,6 +77,10 @@ struct ScanParams {
     float* D;                 // [nq][k]
     int64_t* I;
     int exchange;             // 0: emit local results; 1: exch holds the peer mailboxes
+    // diagnostics (WB_PHASE_TS=1, scripts/phase_times.py): globaltimer stamps of the first consumer thread of every CTA
+    // of query group 0 - [blockIdx.x][16]: 0 start, 1 centroids scored, 2 coarse barrier passed, 3 probes selected,
+    // 4 prologue done, 5 rows done, 6 final sort done, 7 arrived, 8 merge selected (last CTA), 9 results written
+    unsigned long long* phase_ts;
     ExchParams exch;
 };
 
@@ -165,6 +169,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    auto stamp = [&](int i) {
+        if (p.phase_ts && tid == kWarp && blockIdx.y == 0 && blockIdx.x < 1024) p.phase_ts[(size_t)blockIdx.x * 16 + i] = global_ns();
+    };
+    stamp(0);
     const int q0 = blockIdx.y * NQ;
     const int nqv = min(NQ, p.nq - q0);
     const int ld = p.ld, d4 = ld >> 2, ck = p.ck, ck4 = ck >> 2;
@@ -207,7 +215,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             uint32_t* gkeys = p.coarse_keys + (size_t)blockIdx.y * p.nlist;
             coarse_score_slice<kScanThreads>(p.centroids, ld, reinterpret_cast<const float4*>(qs), c0,
                                              min(p.nlist, c0 + per), gkeys, tid);
+            stamp(1);
             group_arrive_wait(&p.coarse_count[blockIdx.y], gridDim.x);
+            stamp(2);
             for (int i = tid; i < nl; i += kScanThreads) ckeys[i] = __ldcg(gkeys + i);
             const int Pn = pow2_ceil(p.nprobe);
             for (int i = p.nprobe + tid; i < Pn; i += kScanThreads) sel[i] = 0ull;
@@ -221,6 +231,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             }
             fence_proxy_async();  // generic-proxy writes to the ring precede the bulk copies that will land there
             __syncthreads();
+            stamp(3);
         }
     }
     if constexpr (GATHER) {
@@ -251,6 +262,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         }
     }
     __syncthreads();
+    stamp(4);
     if constexpr (GATHER) total = prefix[p.nprobe];
     const int64_t ngroups = (total + kGroupRows - 1) / kGroupRows;
     const size_t stage_floats = (size_t)kGroupRows * ck;
@@ -409,7 +421,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         }
         // ---- epilogue: final sort, k best keys of this CTA for each query -------------------
         named_bar_sync(kBarConsumers, kConsumerThreads);
+        stamp(5);
         bitonic_sort_desc<kConsumerThreads>(lists, P, nqv, ctid, kBarConsumers);
+        stamp(6);
         for (int i = ctid; i < nqv * k; i += kConsumerThreads) {
             const int l = i / k, j = i - l * k;
             p.parts[((size_t)(q0 + l) * p.nparts + blockIdx.x) * k + j] = lists[(size_t)l * P + j];
@@ -430,6 +444,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             }
         }
         named_bar_sync(kBarConsumers, kConsumerThreads);
+        stamp(7);
         if (!tail_last) return;
         __threadfence();
         uint64_t* buf = reinterpret_cast<uint64_t*>(ring);  // the ring is idle: every copy has landed and been consumed
@@ -449,6 +464,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                 block_select_topk<kConsumerThreads>(buf, p.S_merge, k, M, [&](int64_t c) { return __ldcg(src + c); },
                                                     &tail_cnt, ctid, kBarConsumers);
             }
+            if (l == 0) stamp(8);
             auto local = [&](int j, float& d, int64_t& id) {
                 const uint64_t key = best[j];
                 d = -FLT_MAX;
@@ -482,6 +498,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                                                        });
             }
         }
+        stamp(9);
     }
 }
 
