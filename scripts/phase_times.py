@@ -1,5 +1,5 @@
 """Where the time of a one-query scan goes: per-CTA %globaltimer stamps (WB_PHASE_TS=1, wb_phase_stamps) of the fused
-scan kernel for a flat store and an IVF index, with the radix-selection merge on and off.  Prints, per case, the
+scan kernel for a flat store and an IVF index, with the heads merge + rank-counting sort on and off.  Prints, per case, the
 median / max over CTAs of every phase boundary relative to the earliest CTA start, and the last CTA's merge time.
     python scripts/phase_times.py"""
 import ctypes as C
@@ -18,7 +18,7 @@ from bench import fill_index_clustered, make_queries  # noqa: E402
 L = _capi.lib()
 dev = torch.device("cuda", 0)
 NAMES = ["start", "centroids scored", "coarse barrier", "probes selected", "prologue done", "rows done", "final sort",
-         "arrived", "merge selected", "results written"]
+         "arrived", "merge selected", "results written", "heads staged", "heads T0", "heads compacted", "heads ranked"]
 
 
 def stamps(idx, qd, k, nprobe, ctas=148):
@@ -38,8 +38,9 @@ def stamps(idx, qd, k, nprobe, ctas=148):
 def report(tag, ts, extra):
     t0 = ts[:, 0].min()
     rec = {"case": tag, **extra}
+    last = int(np.argmax(ts[:, 7]))  # the CTA that arrived last ran the merge; other CTAs hold stale stamps there
     for i, name in enumerate(NAMES):
-        col = ts[:, i]
+        col = ts[:, i] if i < 8 else ts[last:last + 1, i]
         live = col[col > 0]
         if live.size == 0:
             continue
@@ -53,9 +54,9 @@ def main():
         flat = faiss.IndexIDMap(faiss.IndexFlatIP(d))
         centres, _ = fill_index_clustered(flat, 0, n, d, 50, dev)
         q = make_queries(centres, 1, d, 7, dev)
-        for radix in ("0", "1"):
-            os.environ["WB_MERGE_RADIX"] = radix
-            report("flat", stamps(flat, q, 100, 1), {"rows": n, "d": d, "radix_merge": int(radix)})
+        for new in ("0", "1"):
+            os.environ["WB_MERGE_HEADS"] = os.environ["WB_RANK_SORT"] = new
+            report("flat", stamps(flat, q, 100, 1), {"rows": n, "d": d, "heads_merge_and_rank_sort": int(new)})
         del flat
         torch.cuda.empty_cache()
     n, d, nlist = 2_000_000, 512, 1024
@@ -67,9 +68,10 @@ def main():
     fill_index_clustered(ivf, 0, n, d, 50, dev)
     q = make_queries(centres, 1, d, 8, dev)
     for nprobe in (8, 32):
-        for radix in ("0", "1"):
-            os.environ["WB_MERGE_RADIX"] = radix
-            report("ivf", stamps(ivf, q, 100, nprobe), {"rows": n, "nlist": nlist, "nprobe": nprobe, "radix_merge": int(radix)})
+        for new in ("0", "1"):
+            os.environ["WB_MERGE_HEADS"] = os.environ["WB_RANK_SORT"] = new
+            report("ivf", stamps(ivf, q, 100, nprobe), {"rows": n, "nlist": nlist, "nprobe": nprobe,
+                                                        "heads_merge_and_rank_sort": int(new)})
 
 
 if __name__ == "__main__":

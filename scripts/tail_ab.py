@@ -1,5 +1,6 @@
-"""Same-box A/B of the fused scan tail: merge of the per-CTA top-k lists by radix selection (WB_MERGE_RADIX=1, default)
-against the sort-based merge (0).  Device path of one-query searches (CUDA events around back-to-back wb_search_dev
+"""Same-box A/B of the fused scan tail: merge of the per-CTA top-k lists through their heads (WB_MERGE_HEADS=1, default)
+against the sort-based merge (0), and the rank-counting sort of a CTA's [list | queue] (WB_RANK_SORT=1, default) against
+the bitonic sort (0).  Device path of one-query searches (CUDA events around back-to-back wb_search_dev
 calls) on flat stores of several sizes - 1.25M x 768 is one GPU's share of BASELINE config 2 at 8 GPUs - and on an IVF
 index; results must be byte-identical.  One JSON line per case.
     python scripts/tail_ab.py"""
@@ -37,23 +38,25 @@ def device_ms(idx, qd, k, nprobe, reps):
 
 def ab(tag, idx, qd, k, nprobe, reps, extra):
     out = {}
+    arms = {"old": ("0", "0"), "heads": ("1", "0"), "rank": ("0", "1"), "both": ("1", "1")}
     for rnd in range(2):  # A B A B: drift between the arms shows up as a difference between the rounds
-        for radix in ("0", "1"):
-            os.environ["WB_MERGE_RADIX"] = radix
+        for name, (heads, rank) in arms.items():
+            os.environ["WB_MERGE_HEADS"], os.environ["WB_RANK_SORT"] = heads, rank
             ms, D, I = device_ms(idx, qd, k, nprobe, reps)
-            out.setdefault(radix, []).append((ms, D, I))
-    same = all(np.array_equal(out["0"][0][2], r[2]) and np.array_equal(out["0"][0][1].view(np.uint32), r[1].view(np.uint32))
-               for r in out["0"] + out["1"])
+            out.setdefault(name, []).append((ms, D, I))
+    ref = out["old"][0]
+    same = all(np.array_equal(ref[2], r[2]) and np.array_equal(ref[1].view(np.uint32), r[1].view(np.uint32))
+               for v in out.values() for r in v)
     print(json.dumps({"case": tag, **extra, "nq": int(qd.shape[0]), "k": k,
-                      "sort_merge_ms": [round(r[0], 5) for r in out["0"]],
-                      "radix_merge_ms": [round(r[0], 5) for r in out["1"]], "same_bytes": bool(same)}), flush=True)
+                      **{name + "_ms": [round(r[0], 5) for r in v] for name, v in out.items()},
+                      "same_bytes": bool(same)}), flush=True)
 
 
 def main():
     for n, d, reps in ((100_000, 512, 400), (1_250_000, 768, 200), (10_000_000, 768, 40)):
         flat = faiss.IndexIDMap(faiss.IndexFlatIP(d))
         centres, _ = fill_index_clustered(flat, 0, n, d, 50, dev)
-        for nq, k in ((1, 100), (4, 100), (1, 10)):
+        for nq, k in ((1, 100), (4, 100), (1, 10), (1, 250)):
             ab("flat", flat, make_queries(centres, nq, d, 7, dev), k, 1, reps, {"rows": n, "d": d})
         del flat
         torch.cuda.empty_cache()

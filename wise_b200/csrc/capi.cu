@@ -431,6 +431,7 @@ static void apply_scan_cfg(const ScanCfg& c, ScanParams& p) {
     p.single_copy = c.single_copy;
     p.rw = c.RW;
     p.prefetch_idx = env_int("WB_GATHER_PREFETCH", 1);
+    p.rank_sort = c.P <= kConsumerThreads && env_int("WB_RANK_SORT", 1);  // measured: slower than bitonic at P = 512
 }
 
 static cudaError_t launch_scan_coop(const ScanCfg& c, ScanParams& p, dim3 grid, cudaStream_t st) {
@@ -443,13 +444,7 @@ static cudaError_t launch_scan_coop(const ScanCfg& c, ScanParams& p, dim3 grid, 
 }
 
 static int launch_scan(const ScanCfg& c, bool gather, ScanParams& p, dim3 grid, cudaStream_t st) {
-    p.P = c.P;
-    p.ck = c.ck;
-    p.nchunks = c.nchunks;
-    p.stages = c.stages;
-    p.single_copy = c.single_copy;
-    p.rw = c.RW;
-    p.prefetch_idx = env_int("WB_GATHER_PREFETCH", 1);
+    apply_scan_cfg(c, p);
     if (gather) return launch_scan_rw<1, true>(c.RW, p, grid, c.smem, st);
     switch (c.NQ) {
         case 1: return launch_scan_rw<1, false>(c.RW, p, grid, c.smem, st);
@@ -510,29 +505,29 @@ static int ensure_tail_counters(wb_index* h, cudaStream_t st) {
 
 // Can the scan kernel's last CTA run the merge (and the multi-GPU exchange) itself?  The sort buffer and the staged
 // local winners must fit the (then idle) ring.
-static bool tail_fusable(const ScanCfg& c, int k, int64_t nparts, int world, int* S_merge, int* radix_bytes) {
+static bool tail_fusable(const ScanCfg& c, int k, int64_t nparts, int world, int* S_merge, int* heads_bytes) {
     *S_merge = 0;
-    *radix_bytes = 0;
+    *heads_bytes = 0;
     if (env_int("WB_FUSE_TAIL", 1) == 0) return false;
     const size_t ring_bytes = (size_t)c.stages * kConsumerWarps * c.RW * c.ck * 4;
-    // merge by radix selection (radix_select.cuh): all nparts * k keys are staged in the ring, 2-3 histogram passes
-    // pick the k winners; the sort-based merge below is the fallback when they do not fit
-    if (env_int("WB_MERGE_RADIX", 1) && nparts * (int64_t)k < ((int64_t)1 << 24)) {
-        const size_t R = std::max(radix_merge_bytes(nparts * k, k), world > 1 ? radix_merge_bytes((int64_t)world * k, k) : 0);
-        if (R + (size_t)k * 12 + 64 <= ring_bytes) *radix_bytes = (int)R;
-    }
     const int S = std::max(merge_buffer_entries(k, nparts, kConsumerThreads),
                            world > 1 ? merge_buffer_entries(k, world, kConsumerThreads) : 2);
+    if ((size_t)S * 8 + (size_t)k * 12 + 64 > ring_bytes) return false;
     *S_merge = S;
-    if (*radix_bytes) return true;
-    return (size_t)S * 8 + (size_t)k * 12 + 64 <= ring_bytes;
+    // merge through the heads of the sorted lists first (block_merge_heads, merge.cuh); the sort-based merge stays
+    // behind it as the fallback, so both regions must fit
+    if (env_int("WB_MERGE_HEADS", 1) && nparts <= 256) {
+        const HeadsPlan a = heads_plan(k, (int)nparts);
+        if (a.ok && std::max(a.bytes, (size_t)S * 8) + (size_t)k * 12 + 64 <= ring_bytes) *heads_bytes = (int)a.bytes;
+    }
+    return true;
 }
 
-static void set_tail(ScanParams& p, wb_index* h, const ScanCfg& c, int S_merge, int radix_bytes, const int64_t* ids, float* D,
+static void set_tail(ScanParams& p, wb_index* h, const ScanCfg& c, int S_merge, int heads_bytes, const int64_t* ids, float* D,
                      int64_t* I, int k, const ExchParams* ex) {
     p.fuse_tail = 1;
     p.S_merge = S_merge;
-    p.radix_bytes = radix_bytes;
+    p.heads_bytes = heads_bytes;
     p.phase_ts = nullptr;
     if (env_int("WB_PHASE_TS", 0) && h->phase.ensure(kPhaseCtas * 16 * sizeof(unsigned long long)) == 0)
         p.phase_ts = h->phase.as<unsigned long long>();
@@ -546,7 +541,6 @@ static void set_tail(ScanParams& p, wb_index* h, const ScanCfg& c, int S_merge, 
         p.exchange = 1;
         p.exch = *ex;
         p.exch.S = merge_buffer_entries(k, ex->world, kConsumerThreads);
-        p.exch.radix = radix_bytes ? 1 : 0;
     }
 }
 
@@ -574,11 +568,11 @@ static int run_flat_scan(wb_index* h, const float* rows, int64_t nrows, const fl
     p.ld = h->ld;
     p.k = k;
     p.nparts = (int)S;
-    int S_merge = 0, radix_bytes = 0;
-    const bool fuse = tail_fusable(c, k, S, ex ? ex->world : 1, &S_merge, &radix_bytes);
+    int S_merge = 0, heads_bytes = 0;
+    const bool fuse = tail_fusable(c, k, S, ex ? ex->world : 1, &S_merge, &heads_bytes);
     if (fuse) {
         TRY(ensure_tail_counters(h, st));
-        set_tail(p, h, c, S_merge, radix_bytes, ids, ex ? ex->D : D, ex ? ex->I : I, k, ex);
+        set_tail(p, h, c, S_merge, heads_bytes, ids, ex ? ex->D : D, ex ? ex->I : I, k, ex);
     }
     const int evs = (int)(h->ev_count % wb_index::kEvRing);
     if (timed && h->timing) CK(cudaEventRecord(h->ev0[evs], st));
@@ -1444,8 +1438,8 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
     TRY(plan_scan(h, 1, (int)k, true, np, &c));
     int64_t S = nq >= h->sm_count ? 1 : std::max<int64_t>(1, (int64_t)h->sm_count / nq);
     if (ex && (nq > kMaxGridY || !env_int("WB_FUSE_EXCH", 1))) ex = nullptr;
-    int S_merge = 0, radix_bytes = 0;
-    const bool fuse = tail_fusable(c, (int)k, S, ex ? ex->world : 1, &S_merge, &radix_bytes);
+    int S_merge = 0, heads_bytes = 0;
+    const bool fuse = tail_fusable(c, (int)k, S, ex ? ex->world : 1, &S_merge, &heads_bytes);
     // K4 + K5 in one launch (coarse.cuh): a few queries, every CTA resident, the selection scratch fits the idle ring
     const size_t ring_bytes = (size_t)c.stages * kConsumerWarps * c.RW * c.ck * 4;
     bool fuse_coarse = fuse && h->coop_ok && nq <= env_int("WB_IVF_FUSE_COARSE_MAXQ", 4) && S * nq <= h->sm_count &&
@@ -1476,7 +1470,7 @@ static int search_dev_impl(wb_index* h, int64_t nq, const float* q_ld /* [nq, ld
         p.nprobe = np;
         if (fuse) {
             TRY(ensure_tail_counters(h, st));
-            set_tail(p, h, c, S_merge, radix_bytes, h->ids, ex ? ex->D : D, ex ? ex->I : I, (int)k, ex);
+            set_tail(p, h, c, S_merge, heads_bytes, h->ids, ex ? ex->D : D, ex ? ex->I : I, (int)k, ex);
         }
         if (fuse_coarse) {
             TRY(h->ckeys.ensure((size_t)nq * h->nlist * sizeof(uint32_t)));
@@ -2156,7 +2150,6 @@ static int launch_exchange_kernel(wb_exchange* ex, ExchParams& p, const float* D
                                   cudaStream_t st) {
     p.D_local = D_local;
     p.I_local = I_local;
-    p.radix = 0;  // (the stand-alone kernel keeps the sort-based merge; its buffer is p.S keys)
     p.S = merge_buffer_entries(p.k, p.world);
     static thread_local bool attr_done[64] = {};
     if (ex->device >= 64 || !attr_done[ex->device]) {

@@ -178,4 +178,87 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t* keys, int P, int nli
     if (P < 64) bitonic_block_sync<NT>(bar_id);
 }
 
+// ---- rank counting ---------------------------------------------------------------------------------------------
+// Non-empty keys (0 = empty) are distinct, so "number of larger keys" IS the position of a key in descending order.
+// The tail of a scan runs on the 8 warps of ONE SM - two warps per scheduler, every dependent instruction exposed - so
+// the loops below rank 4 keys per pass over the array with 4 independent loads in flight (a warp that ranked one key
+// at a time with a rolled loop spent ~270 ns per key; an out-of-line copy of this routine was slower than the inlined
+// one: per-phase %globaltimer stamps in profiles/r02/NOTES.md).
+struct Rank4 {
+    int r[4];
+};
+// Ranks of k0..k3 among the n keys of the shared-memory array `arr`; the lanes of the calling warp split the array,
+// every lane gets the ranks.
+__device__ __forceinline__ Rank4 warp_rank4_desc(const uint64_t* arr, int n, uint64_t k0, uint64_t k1, uint64_t k2,
+                                                 uint64_t k3) {
+    const int lane = threadIdx.x & 31;
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int u0 = 0; u0 < n; u0 += 128) {
+        uint64_t a[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int u = u0 + x * 32 + lane;
+            a[x] = u < n ? arr[u] : 0ull;
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            c0 += a[x] > k0;
+            c1 += a[x] > k1;
+            c2 += a[x] > k2;
+            c3 += a[x] > k3;
+        }
+    }
+    Rank4 out;
+    out.r[0] = (int)__reduce_add_sync(0xffffffffu, (unsigned)c0);
+    out.r[1] = (int)__reduce_add_sync(0xffffffffu, (unsigned)c1);
+    out.r[2] = (int)__reduce_add_sync(0xffffffffu, (unsigned)c2);
+    out.r[3] = (int)__reduce_add_sync(0xffffffffu, (unsigned)c3);
+    return out;
+}
+
+// dst[rank] = key for every non-empty key of src[0, n) whose rank is below `limit`; `nwarps` whole warps (warp index
+// `warp`).  src / dst are shared memory and must not overlap; the caller zero-fills dst and synchronises around the call.
+__device__ __forceinline__ void block_rank_scatter(const uint64_t* src, int n, uint64_t* dst, int limit, int warp,
+                                                   int nwarps) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t* a = src;
+    for (int t0 = warp * 4; t0 < n; t0 += nwarps * 4) {
+        uint64_t key = 0ull;  // lane b < 4 holds key t0 + b
+        if (lane < 4 && t0 + lane < n) key = src[t0 + lane];
+        const uint64_t k0 = __shfl_sync(0xffffffffu, key, 0), k1 = __shfl_sync(0xffffffffu, key, 1),
+                       k2 = __shfl_sync(0xffffffffu, key, 2), k3 = __shfl_sync(0xffffffffu, key, 3);
+        const Rank4 rk = warp_rank4_desc(a, n, k0, k1, k2, k3);
+        const int myr = lane == 0 ? rk.r[0] : lane == 1 ? rk.r[1] : lane == 2 ? rk.r[2] : rk.r[3];
+        if (lane < 4 && key && myr < limit) dst[myr] = key;
+    }
+}
+
+// In-place sort of ONE array of P <= NT keys, descending (empty keys last): warp w ranks the keys [32 w, 32 w + 32),
+// lane i keeps (key, rank) of key 32 w + i in registers across the barrier that separates the reads from the scatter.
+// Three barriers instead of the 36 compare-exchange steps of a 256-key bitonic sort.
+template <int NT>
+__device__ __forceinline__ void rank_sort_desc(uint64_t* keys, int P, int tid, int bar_id) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint64_t* a = keys;
+    uint64_t my_key = 0ull;
+    int my_rank = 0;
+    if (warp * 32 < P) {  // (warp-uniform)
+        const uint64_t own = warp * 32 + lane < P ? keys[warp * 32 + lane] : 0ull;
+#pragma unroll 1
+        for (int b0 = 0; b0 < 32; b0 += 4) {
+            const uint64_t k0 = __shfl_sync(0xffffffffu, own, b0), k1 = __shfl_sync(0xffffffffu, own, b0 + 1),
+                           k2 = __shfl_sync(0xffffffffu, own, b0 + 2), k3 = __shfl_sync(0xffffffffu, own, b0 + 3);
+            const Rank4 rk = warp_rank4_desc(a, P, k0, k1, k2, k3);
+            const int x = lane - b0;
+            if (x >= 0 && x < 4) my_rank = x == 0 ? rk.r[0] : x == 1 ? rk.r[1] : x == 2 ? rk.r[2] : rk.r[3];
+        }
+        my_key = own;
+    }
+    bitonic_block_sync<NT>(bar_id);
+    if (tid < P) keys[tid] = 0ull;
+    bitonic_block_sync<NT>(bar_id);
+    if (my_key) keys[my_rank] = my_key;
+    bitonic_block_sync<NT>(bar_id);
+}
+
 }  // namespace wb

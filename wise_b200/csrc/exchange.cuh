@@ -28,7 +28,6 @@ struct ExchParams {
     int64_t nq;
     int k;
     int S;                          // sort buffer entries
-    int radix;                      // 1: merge by radix selection (radix_select.cuh); buf holds radix_merge_bytes(world * k, k)
     uint32_t seq;                   // call sequence number (> 0)
     const float* D_local;           // [nq][k] this rank's results (exchange_merge_kernel only)
     const int64_t* I_local;
@@ -107,18 +106,16 @@ __device__ __forceinline__ void exch_push_wait_merge(const ExchParams& p, int64_
             reinterpret_cast<const volatile int64_t*>(reg + p.flags_bytes + p.cap_entries * sizeof(float));
         return vI[q * k + slot] >= 0 ? make_key(vD[q * k + slot], (uint32_t)c) : 0ull;
     };
-    const uint64_t* best = buf;
-    if (p.radix) {
-        best = block_topk_radix<NT>(reinterpret_cast<unsigned char*>(buf), (int)M, k, [&](int c) { return load((int64_t)c); },
-                                    tid, bar_id);
-    } else if (!block_select_topk_lists<NT>(buf, p.S, k, p.world, [&](int l, int r) { return load((int64_t)l * k + r); },
-                                            cnt, tid, bar_id)) {
+    // (block_merge_heads was tried here too: with 2 ranks the sort-based merge already sorts all 2k keys in one
+    // 256-key pass and the heads variant cost 4 us more per search - profiles/r02/NOTES.md)
+    if (!block_select_topk_lists<NT>(buf, p.S, k, p.world, [&](int l, int r) { return load((int64_t)l * k + r); }, cnt,
+                                     tid, bar_id)) {
         sel_sync<NT>(bar_id);
         block_select_topk<NT>(buf, p.S, k, M, load, cnt, tid, bar_id);
     }
     const unsigned char* myreg0 = exch_region(p, p.rank, b, 0);
     for (int j = tid; j < k; j += NT) {
-        const uint64_t key = best[j];
+        const uint64_t key = buf[j];
         float d = -FLT_MAX;
         int64_t id = -1;
         if (key) {

@@ -146,6 +146,138 @@ __device__ __forceinline__ bool block_select_topk_lists(uint64_t* buf, int S, in
     return true;
 }
 
+// ---- merge of sorted lists through their heads ---------------------------------------------------------------
+// Top-k of `nlists` SORTED (descending, 0-padded) lists, load(list, rank) -> key, without sorting anything large.
+// The k-th largest of the first j entries of every list (nlists * j >= 1.25 k of them) is a lower bound T0 of the final
+// k-th key - at least k keys are >= T0 - and a sharp one: with the winners spread over 148 lists, ~1.7 k keys pass it.
+// The candidates >= T0 are a short prefix of every list; they are found in the J staged entries of each list, compacted,
+// and ranked by counting (rank = number of larger candidates = output position: the keys are distinct).  Three
+// broadcast-read loops over a few hundred keys and five barriers replace a 1024-key bitonic sort, per-list boundary
+// loads from L2, a binary search and a second sort (12.4 us per search in the last CTA of a scan; NOTES.md).
+// Returns false (uniform, nothing written) when a list may reach deeper than its staged prefix or the candidates
+// overflow - winners clustered in a few lists - and the caller runs block_select_topk_lists instead.
+constexpr int kHeadsCandCap = 1024;
+struct HeadsPlan {
+    int j, J, lgJ, stride, ok;
+    size_t bytes;
+};
+__host__ __device__ inline HeadsPlan heads_plan(int k, int nlists) {
+    HeadsPlan P{};
+    if (k < 1 || k > 128 || nlists < 1 || nlists > 256) return P;  // (k = 250: 8 us slower than the sort-based merge)
+    int j = (k + k / 4 + nlists - 1) / nlists;  // heads per list that define T0
+    if (j < 1) j = 1;
+    if (j > k) j = k;
+    if ((int64_t)nlists * j > 256) return P;
+    int lgJ = 3;                                // staged entries per list: a power of two >= max(2 j, 8)
+    while ((1 << lgJ) < 2 * j) ++lgJ;
+    P.j = j;
+    P.lgJ = lgJ;
+    P.J = 1 << lgJ;                             // (entries beyond k are staged as empty)
+    P.stride = P.J | 1;                         // odd stride: the per-list scans of step 3 spread over the banks
+    P.ok = 1;
+    // staged[nlists][stride] | heads[nlists * j] | hsorted[k] | cand[cap] | out[k] | overflow flag
+    P.bytes = (((size_t)nlists * P.stride + (size_t)nlists * j + kHeadsCandCap + 2 * (size_t)k) * 8 + 64 + 15) & ~(size_t)15;
+    return P;
+}
+
+template <int NT, class Load2>
+__device__ __forceinline__ bool block_merge_heads(unsigned char* region, int k, int nlists, Load2 load, int* cnt, int tid,
+                                                  int bar_id, const uint64_t** best_out,
+                                                  unsigned long long* ts = nullptr /* diagnostics: 4 phase stamps */) {
+    auto stamp = [&](int i) {
+        if (ts && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            ts[i] = t;
+        }
+    };
+    const HeadsPlan hp = heads_plan(k, nlists);
+    if (!hp.ok) return false;  // (uniform; the host only sets the mode when the plan is valid)
+    const int j = hp.j, J = hp.J, lgJ = hp.lgJ, stride = hp.stride, nh = nlists * j;
+    const int warp = tid >> 5, lane = tid & 31;
+    uint64_t* staged = reinterpret_cast<uint64_t*>(region);
+    uint64_t* heads = staged + (size_t)nlists * stride;
+    uint64_t* hsorted = heads + nh;
+    uint64_t* cand = hsorted + k;
+    uint64_t* out = cand + kHeadsCandCap;
+    int* ovf_s = reinterpret_cast<int*>(out + k);                // [0] overflow flag
+    // 1. stage the first J entries of every list (the first j of them also densely: the heads).  All loads of a thread
+    //    are issued before its first store: the keys come from L2 at ~0.5 us per round trip.
+    for (int base = 0; base < (nlists << lgJ); base += NT * 8) {
+        uint64_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * NT + tid;
+            const int l = i >> lgJ, r = i & (J - 1);
+            v[u] = (l < nlists && r < k) ? load(l, r) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * NT + tid;
+            const int l = i >> lgJ, r = i & (J - 1);
+            if (l < nlists) {
+                staged[l * stride + r] = v[u];
+                if (r < j) heads[l * j + r] = v[u];
+            }
+        }
+    }
+    for (int i = tid; i < 2 * k; i += NT) {  // hsorted, out
+        if (i < k) hsorted[i] = 0ull;
+        else out[i - k] = 0ull;
+    }
+    if (tid == 0) {
+        *cnt = 0;
+        *ovf_s = 0;
+    }
+    sel_sync<NT>(bar_id);
+    stamp(0);
+    // 2. T0 = the k-th largest of the heads (0 if fewer than k heads are non-empty: everything is a candidate)
+    block_rank_scatter(heads, nh, hsorted, k, warp, NT / 32);
+    sel_sync<NT>(bar_id);
+    stamp(1);
+    // 3. candidates: the prefix >= T0 of every list (one atomicAdd per warp: the lanes' counts are scanned first)
+    const uint64_t T0 = hsorted[k - 1];
+    for (int l0 = 0; l0 < nlists; l0 += NT) {  // (uniform trip count: whole warps take part in the shuffles)
+        const int l = l0 + tid;
+        const uint64_t* row = staged + (l < nlists ? l : 0) * stride;
+        int c = 0;
+        if (l < nlists) {
+            while (c < J && row[c] != 0ull && row[c] >= T0) ++c;
+            if (c == J && J < k) *ovf_s = 1;  // the list may hold more candidates than were staged
+        }
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int wtot = __shfl_sync(0xffffffffu, inc, 31);
+        int wbase = 0;
+        if (lane == 31 && wtot) wbase = atomicAdd(cnt, wtot);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        const int off = wbase + inc - c;
+        if (c) {
+            if (off + c <= kHeadsCandCap) {
+                for (int r = 0; r < c; ++r) cand[off + r] = row[r];
+            } else {
+                *ovf_s = 1;
+            }
+        }
+    }
+    sel_sync<NT>(bar_id);
+    stamp(2);
+    if (*ovf_s) {
+        sel_sync<NT>(bar_id);  // everyone has read the flag before the caller's fallback reuses the region
+        return false;
+    }
+    // 4. rank by counting: position = number of larger candidates
+    block_rank_scatter(cand, *cnt, out, k, warp, NT / 32);
+    sel_sync<NT>(bar_id);
+    stamp(3);
+    *best_out = out;
+    return true;
+}
+
 template <bool FROM_KEYS>
 __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const MergeParams p) {
     extern __shared__ __align__(16) unsigned char smem_merge[];

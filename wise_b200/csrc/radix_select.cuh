@@ -1,13 +1,12 @@
 // radix_select.cuh - exact block-level top-k of n DISTINCT 64-bit keys (0 = empty slot) without sorting them.
 //
-// Used where a thread block must pick k winners out of many more candidates and only the winners need an order:
-//   * the merge of the per-CTA top-k lists at the tail of a scan (K3 inside K1 / K5: 148 x k keys -> k), and the
-//     merge of the per-rank rows after the NVLink exchange - faiss's result-handler merge / heap_reorder
-//     [faiss-upstream], reached from /root/reference/src/index/feature_search_index.py:113;
-//   * the top-nprobe of the centroid scores in the fused coarse quantizer (coarse.cuh).
-// A bitonic sort of the 1024-key merge buffer cost the LAST CTA of every scan ~20 us (ncu: the SM that merges is
-// active for 107k cycles of a launch whose other SMs finish after 57k); selection needs 2-3 cheap passes instead:
-// every pass histograms the keys of the current range [lo, hi] into <= 1024 equal-width bins, takes every bin above the
+// Used where a thread block must pick k winners out of many more UNORDERED candidates and only the winners need an
+// order: the top-nprobe of the centroid scores in the fused coarse quantizer (coarse.cuh) - the selection inside faiss
+// quantizer->search [faiss-upstream], reached from /root/reference/src/index/feature_search_index.py:113.
+// (Tried for the merge of the per-CTA top-k lists at the tail of a scan as well: 148 x 100 staged keys took 16.6 us
+// against 12.4 us for the sort-based merge, which touches only the heads of the SORTED lists - profiles/r02/NOTES.md;
+// that merge is block_merge_heads in merge.cuh.)
+// Every pass histograms the keys of the current range [lo, hi] into <= 1024 equal-width bins, takes every bin above the
 // one that holds the need-th largest key, and either finishes (that bin is taken whole) or recurses into it.  The first
 // range is [min key, max key], so the bins resolve the score distribution at once; a range shrinks by >= 2^10 per pass
 // and a width-1 bin holds one key, so the loop ends after at most 7 passes.  The k winners are then bitonic-sorted
@@ -159,27 +158,6 @@ __device__ __forceinline__ int block_radix_select(int n, int need0, KeyAt key_at
         rs_sync<NT>(bar_id);
     }
     return need_total;
-}
-
-// Shared-memory region of a key merge: keys[M] | best[pow2_ceil(k)] | selection scratch.
-__host__ __device__ inline size_t radix_merge_bytes(int64_t M, int k) {
-    return (((size_t)M + (size_t)pow2_ceil(k)) * 8 + kRadixScratchBytes + 15) & ~(size_t)15;
-}
-
-// Top-k of the M keys load(i) (0 = empty): stages them in `region` (radix_merge_bytes(M, k) bytes of shared memory),
-// selects, sorts the winners.  Returns the pow2_ceil(k) sorted (descending, zero-padded) best keys, inside `region`.
-template <int NT, class Load>
-__device__ __forceinline__ uint64_t* block_topk_radix(unsigned char* region, int M, int k, Load load, int tid, int bar_id) {
-    uint64_t* keys = reinterpret_cast<uint64_t*>(region);
-    const int Pk = pow2_ceil(k);
-    uint64_t* best = keys + M;
-    for (int i = tid; i < M; i += NT) keys[i] = load(i);
-    for (int i = tid; i < Pk; i += NT) best[i] = 0ull;
-    rs_sync<NT>(bar_id);
-    block_radix_select<NT>(M, k, [&](int i) { return keys[i]; }, RadixScratch(reinterpret_cast<unsigned char*>(best + Pk)),
-                           best, tid, bar_id);
-    if (Pk >= 2) bitonic_sort_desc<NT>(best, Pk, 1, tid, bar_id);
-    return best;
 }
 
 }  // namespace wb

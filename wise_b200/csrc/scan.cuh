@@ -66,7 +66,8 @@ struct ScanParams {
     // merged rows to the peer GPUs' mailboxes, waits for theirs and emits the GLOBAL top-k (exchange.cuh).
     int fuse_tail;
     int S_merge;              // sort-buffer entries of the fused merge (the idle ring holds them)
-    int radix_bytes;          // > 0: the fused merge selects by radix (radix_select.cuh) in this many bytes of the ring
+    int heads_bytes;          // > 0: the fused merge tries block_merge_heads (merge.cuh) in this many bytes of the ring
+    int rank_sort;            // 1: [list | queue] of one query is sorted by rank counting (P <= 512), not bitonic
     unsigned int* tail_count; // [gridDim.y] arrival counters, zero between launches (the last CTA resets its own)
     // dynamic row-group scheduling (fused-tail launches with whole-row stages): CTAs draw the next row group from
     // group_count[blockIdx.y] instead of striding by gridDim.x.  SMs stream at slightly different rates (ncu: the
@@ -79,7 +80,8 @@ struct ScanParams {
     int exchange;             // 0: emit local results; 1: exch holds the peer mailboxes
     // diagnostics (WB_PHASE_TS=1, scripts/phase_times.py): globaltimer stamps of the first consumer thread of every CTA
     // of query group 0 - [blockIdx.x][16]: 0 start, 1 centroids scored, 2 coarse barrier passed, 3 probes selected,
-    // 4 prologue done, 5 rows done, 6 final sort done, 7 arrived, 8 merge selected (last CTA), 9 results written
+    // 4 prologue done, 5 rows done, 6 final sort done, 7 arrived, 8 merge selected (last CTA), 9 results written,
+    // 10-13 inside block_merge_heads: staged, T0 found, candidates compacted, ranked
     unsigned long long* phase_ts;
     ExchParams exch;
 };
@@ -406,7 +408,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                 }
             }
             if (named_bar_or(kBarConsumers, kConsumerThreads, hw)) {
-                bitonic_sort_desc<kConsumerThreads>(lists, P, nqv, ctid, kBarConsumers);
+                if (NQ == 1 && p.rank_sort) rank_sort_desc<kConsumerThreads>(lists, P, ctid, kBarConsumers);
+                else bitonic_sort_desc<kConsumerThreads>(lists, P, nqv, ctid, kBarConsumers);
                 for (int i = ctid; i < nqv * qcap; i += kConsumerThreads) {
                     const int l = i / qcap, j = i - l * qcap;
                     lists[(size_t)l * P + k + j] = 0ull;
@@ -422,7 +425,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         // ---- epilogue: final sort, k best keys of this CTA for each query -------------------
         named_bar_sync(kBarConsumers, kConsumerThreads);
         stamp(5);
-        bitonic_sort_desc<kConsumerThreads>(lists, P, nqv, ctid, kBarConsumers);
+        if (NQ == 1 && p.rank_sort) rank_sort_desc<kConsumerThreads>(lists, P, ctid, kBarConsumers);
+        else bitonic_sort_desc<kConsumerThreads>(lists, P, nqv, ctid, kBarConsumers);
         stamp(6);
         for (int i = ctid; i < nqv * k; i += kConsumerThreads) {
             const int l = i / k, j = i - l * k;
@@ -453,16 +457,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             const uint64_t* src = p.parts + (size_t)q * p.nparts * k;
             const int64_t M = (int64_t)p.nparts * k;
             const uint64_t* best = buf;
-            if (p.radix_bytes) {
-                // no sort of the candidates: 2-3 histogram passes pick the k winners, only those are sorted
-                best = block_topk_radix<kConsumerThreads>(reinterpret_cast<unsigned char*>(ring), (int)M, k,
-                                                          [&](int i) { return __ldcg(src + i); }, ctid, kBarConsumers);
-            } else if (!block_select_topk_lists<kConsumerThreads>(
-                           buf, p.S_merge, k, p.nparts, [&](int li, int r) { return __ldcg(src + (size_t)li * k + r); },
-                           &tail_cnt, ctid, kBarConsumers)) {
+            auto load2 = [&](int li, int r) { return __ldcg(src + (size_t)li * k + r); };
+            if (!(p.heads_bytes && block_merge_heads<kConsumerThreads>(reinterpret_cast<unsigned char*>(ring), k, p.nparts, load2,
+                                                                       &tail_cnt, ctid, kBarConsumers, &best,
+                                                                       p.phase_ts && blockIdx.y == 0 && blockIdx.x < 1024
+                                                                           ? p.phase_ts + (size_t)blockIdx.x * 16 + 10
+                                                                           : nullptr))) {
+                best = buf;
                 named_bar_sync(kBarConsumers, kConsumerThreads);
-                block_select_topk<kConsumerThreads>(buf, p.S_merge, k, M, [&](int64_t c) { return __ldcg(src + c); },
-                                                    &tail_cnt, ctid, kBarConsumers);
+                if (!block_select_topk_lists<kConsumerThreads>(buf, p.S_merge, k, p.nparts, load2, &tail_cnt, ctid,
+                                                               kBarConsumers)) {
+                    named_bar_sync(kBarConsumers, kConsumerThreads);
+                    block_select_topk<kConsumerThreads>(buf, p.S_merge, k, M, [&](int64_t c) { return __ldcg(src + c); },
+                                                        &tail_cnt, ctid, kBarConsumers);
+                }
             }
             if (l == 0) stamp(8);
             auto local = [&](int j, float& d, int64_t& id) {
@@ -486,8 +494,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                 named_bar_sync(kBarConsumers, kConsumerThreads);  // buf is reused by the next query
             } else {
                 // the local winners move to the second half of the buffer region: the exchange merge sorts in `buf`
-                float* ld_s = p.radix_bytes ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ring) + p.radix_bytes)
-                                            : reinterpret_cast<float*>(buf + p.S_merge);
+                float* ld_s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ring) +
+                                                       max((size_t)p.S_merge * 8, (size_t)p.heads_bytes));
                 int64_t* li_s = reinterpret_cast<int64_t*>(ld_s + ((k + 1) & ~1));
                 for (int j = ctid; j < k; j += kConsumerThreads) local(j, ld_s[j], li_s[j]);
                 named_bar_sync(kBarConsumers, kConsumerThreads);
