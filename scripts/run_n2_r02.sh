@@ -6,7 +6,7 @@ timeout 600 python -m pytest tests/test_multigpu_gpu.py -m gpu -q > $O/test_mult
 echo "multigpu tests rc=$?" | tee $O/status.txt
 tail -4 $O/test_multigpu.log
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533"
-for H in 1 0 1 0; do
+for H in 1 0; do
   WB_MERGE_HEADS=$H WB_RANK_SORT=$H timeout 300 $T bench.py --gpus 2 --steps 50 --warmup 5 --no-cpu-baseline --secondary none > $O/bench_n2_heads$H.json 2> $O/bench_n2_heads$H.err
   echo "bench heads=$H rc=$?" | tee -a $O/status.txt
   python - <<P
