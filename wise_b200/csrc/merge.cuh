@@ -180,7 +180,7 @@ __host__ __device__ inline HeadsPlan heads_plan(int k, int nlists) {
     return P;
 }
 
-template <int NT, class Load2>
+template <int NT, bool WARP_RANK, class Load2>
 __device__ __forceinline__ bool block_merge_heads(unsigned char* region, int k, int nlists, Load2 load, int* cnt, int tid,
                                                   int bar_id, const uint64_t** best_out,
                                                   unsigned long long* ts = nullptr /* diagnostics: 4 phase stamps */) {
@@ -270,8 +270,22 @@ __device__ __forceinline__ bool block_merge_heads(unsigned char* region, int k, 
         sel_sync<NT>(bar_id);  // everyone has read the flag before the caller's fallback reuses the region
         return false;
     }
-    // 4. rank by counting: position = number of larger candidates
-    block_rank_scatter(cand, *cnt, out, k, warp, NT / 32);
+    // 4. rank by counting: position = number of larger candidates.  Two codings, chosen per kernel by measurement
+    //    (~170 candidates; NOTES.md section 6): one thread per candidate with broadcast loads - 2.0-2.9 us in the flat
+    //    scan kernel but 5.2 us in the gather instantiation - or block_rank_scatter (lanes split the array, a warp
+    //    ranks 4 keys per pass) - 4.2 us in the flat kernel, 3.4 us in the gather one.
+    if constexpr (WARP_RANK) {
+        block_rank_scatter(cand, *cnt, out, k, warp, NT / 32);
+    } else {
+        const int C = *cnt;
+        for (int t = tid; t < C; t += NT) {
+            const uint64_t key = cand[t];
+            int rank = 0;
+#pragma unroll 8
+            for (int u = 0; u < C; ++u) rank += cand[u] > key;
+            if (rank < k) out[rank] = key;
+        }
+    }
     sel_sync<NT>(bar_id);
     stamp(3);
     *best_out = out;

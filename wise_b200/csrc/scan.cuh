@@ -220,16 +220,40 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             stamp(1);
             group_arrive_wait(&p.coarse_count[blockIdx.y], gridDim.x);
             stamp(2);
-            for (int i = tid; i < nl; i += kScanThreads) ckeys[i] = __ldcg(gkeys + i);
+            // (8 loads in flight per thread: one at a time, the L2 round trips of a 4096-list table alone took ~7 us)
+            for (int base = 0; base < nl; base += kScanThreads * 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = base + u * kScanThreads + tid;
+                    v[u] = i < nl ? __ldcg(gkeys + i) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = base + u * kScanThreads + tid;
+                    if (i < nl) ckeys[i] = v[u];
+                }
+            }
             const int Pn = pow2_ceil(p.nprobe);
             for (int i = p.nprobe + tid; i < Pn; i += kScanThreads) sel[i] = 0ull;
             __syncthreads();
             block_radix_select<kScanThreads>(nl, p.nprobe, [&](int i) { return coarse_key64(ckeys[i], (uint32_t)i); },
                                              RadixScratch(scratch + CL.scratch), sel, tid, -1);
-            if (Pn >= 2) bitonic_sort_desc<kScanThreads>(sel, Pn, 1, tid, -1);
-            for (int j = tid; j < p.nprobe; j += kScanThreads) {
-                const uint64_t key = sel[j];
-                pbase[j] = (key >> 32) ? (int64_t)key_pos(key) : (int64_t)-1;  // read back as the list id below
+            auto probe_of = [](uint64_t key) { return (key >> 32) ? (int64_t)key_pos(key) : (int64_t)-1; };
+            if (p.nprobe <= 128) {
+                // few winners: the rank of a key among them (keys are distinct) is its place in the probe order
+                for (int t0 = warp * 4; t0 < p.nprobe; t0 += (kScanThreads / 32) * 4) {
+                    uint64_t key = 0ull;
+                    if (lane < 4 && t0 + lane < p.nprobe) key = sel[t0 + lane];
+                    const Rank4 rk = warp_rank4_desc(sel, p.nprobe, __shfl_sync(0xffffffffu, key, 0),
+                                                     __shfl_sync(0xffffffffu, key, 1), __shfl_sync(0xffffffffu, key, 2),
+                                                     __shfl_sync(0xffffffffu, key, 3));
+                    const int myr = lane == 0 ? rk.r[0] : lane == 1 ? rk.r[1] : lane == 2 ? rk.r[2] : rk.r[3];
+                    if (lane < 4 && t0 + lane < p.nprobe) pbase[myr] = probe_of(key);  // read back as the list id below
+                }
+            } else {
+                bitonic_sort_desc<kScanThreads>(sel, Pn, 1, tid, -1);
+                for (int j = tid; j < p.nprobe; j += kScanThreads) pbase[j] = probe_of(sel[j]);
             }
             fence_proxy_async();  // generic-proxy writes to the ring precede the bulk copies that will land there
             __syncthreads();
@@ -458,7 +482,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             const int64_t M = (int64_t)p.nparts * k;
             const uint64_t* best = buf;
             auto load2 = [&](int li, int r) { return __ldcg(src + (size_t)li * k + r); };
-            if (!(p.heads_bytes && block_merge_heads<kConsumerThreads>(reinterpret_cast<unsigned char*>(ring), k, p.nparts, load2,
+            if (!(p.heads_bytes && block_merge_heads<kConsumerThreads, GATHER>(reinterpret_cast<unsigned char*>(ring), k, p.nparts, load2,
                                                                        &tail_cnt, ctid, kBarConsumers, &best,
                                                                        p.phase_ts && blockIdx.y == 0 && blockIdx.x < 1024
                                                                            ? p.phase_ts + (size_t)blockIdx.x * 16 + 10
