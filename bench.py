@@ -19,7 +19,9 @@ reference serves, /root/reference/api/routes.py:1407) over the whole database:
            planted exact duplicate (last row == row 0, on different ranks when N > 1) ties in insertion order
   secondary (N = 1) the same measurement at batch 16 (K2, HBM roofline) and batch 1024 (K2 256-query blocks,
            tensor roofline against the TF32 peak measured live with the library's own MMA shape), each with its own
-           parity_check; batch 1024 also carries the BLAS-path CPU baseline
+           parity_check; batch 1024 also carries the BLAS-path CPU baseline; `ivf_one_query`: IndexIVFFlat 2M x 512,
+           nlist 1024, ONE query per call (the product's case): device path and host call at nprobe 8 / 32 with the
+           coarse quantizer inside the list-scan launch and as its own launch, byte-identity, exhaustive parity check
   cpu_baseline  the faiss-equivalent C restatement (oracle/cpu_flat.c) on this box's host cores,
            on a bounded row sample, scaled linearly (faiss itself is not installable: BASELINE.md 3)
 N > 1: the 10M rows are split into N contiguous shards (strong scaling), one process per GPU; the exchange of
@@ -392,6 +394,109 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------
+def ivf_one_query_secondary(device, k):
+    """secondary.ivf_one_query (N = 1): the product's IVF case - ONE query per call (/root/reference/api/routes.py:1407 with
+    nprobe from config, :899-902) - on IndexIVFFlat 2M x 512, nlist 1024.  Device path (CUDA events around 200
+    back-to-back searches) with the coarse quantizer inside the list-scan launch and as its own launch, the host API
+    (numpy in, numpy out), byte-identity of the two, and an exhaustive check (nprobe = nlist) of the returned (D, I)
+    against an fp64 pass over regenerated rows.  Any failure is reported in the entry instead of raising: this
+    measurement must never cost the headline line."""
+    import torch
+    from wise_b200 import _capi, faiss_compat as faiss
+    L = _capi.lib()
+    n, d, nlist, seed, chunk = 2_000_000, 512, 1024, 50, 500_000
+    out = {"config": {"workload": f"IndexIVFFlat nlist={nlist} top-{k} over {n}x{d} fp32, query batch 1",
+                      "centroids": "the first nlist rows of the store (no training: searches are what is timed)"}}
+    saved = os.environ.get("WB_IVF_FUSE_COARSE")
+    try:
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        centres = torch.nn.functional.normalize(torch.randn(NCENTRES, d, device=device, generator=gen), dim=1)
+
+        def rows_of(s):  # the chunk fill_index_clustered adds at row s
+            e = min(n, s + chunk)
+            g2 = torch.Generator(device=device)
+            g2.manual_seed(seed * 1_000_003 + s)
+            j = torch.randint(0, NCENTRES, (e - s,), device=device, generator=g2)
+            x = centres[j] + 0.6 * torch.randn(e - s, d, device=device, generator=g2) / (d ** 0.5)
+            return torch.nn.functional.normalize(x, dim=1).contiguous()
+
+        ivf = faiss.IndexIVFFlat(faiss.IndexFlatIP(d), d, nlist, faiss.METRIC_INNER_PRODUCT)
+        ivf.set_centroids(rows_of(0)[:nlist].cpu().numpy())
+        fill_index_clustered(ivf, 0, n, d, seed, device, chunk=chunk)
+        q = make_queries(centres, 1, d, 8, device)
+        qh = q.cpu().numpy()
+        st = torch.cuda.current_stream().cuda_stream
+        D = torch.empty(1, k, device=device)
+        I = torch.empty(1, k, dtype=torch.int64, device=device)
+
+        def device_ms(nprobe, reps=200):
+            call = lambda: _capi.check(L.wb_search_dev(ivf._h, 1, q.data_ptr(), k, nprobe, D.data_ptr(), I.data_ptr(), st))
+            for _ in range(20):
+                call()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                call()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps, D.cpu().numpy().copy(), I.cpu().numpy().copy()
+
+        per = {}
+        for nprobe in (8, 32):
+            ivf.nprobe = nprobe
+            os.environ["WB_IVF_FUSE_COARSE"] = "0"
+            two_ms, D2, I2 = device_ms(nprobe)
+            os.environ["WB_IVF_FUSE_COARSE"] = "1"
+            f0, l0 = L.wb_ivf_fused_searches(ivf._h), L.wb_launch_count(ivf._h)
+            one_ms, D1, I1 = device_ms(nprobe)
+            nsearch = 220
+            fused, launches = L.wb_ivf_fused_searches(ivf._h) - f0, L.wb_launch_count(ivf._h) - l0
+            wall = []
+            for _ in range(220):
+                t0 = time.perf_counter()
+                Dh, Ih = ivf.search(qh, k)
+                wall.append(time.perf_counter() - t0)
+            per[f"nprobe{nprobe}"] = {
+                "device_ms_per_search": one_ms, "device_ms_two_launches": two_ms,
+                "e2e_ms_per_call_median": float(np.median(wall[20:]) * 1e3), "launches_per_search": launches / nsearch,
+                "fused_searches": int(fused), "same_bytes_as_two_launches": bool(
+                    np.array_equal(I1, I2) and np.array_equal(D1.view(np.uint32), D2.view(np.uint32))
+                    and np.array_equal(Ih, I1) and np.array_equal(Dh.view(np.uint32), D1.view(np.uint32)))}
+        out.update(per)
+        # exhaustive setting: every list probed -> the result must be the exact top-k of all rows
+        ivf.nprobe = nlist
+        Dx, Ix = ivf.search(qh, k)
+        best_s = torch.full((0,), 0.0, dtype=torch.float64, device=device)
+        best_i = torch.zeros((0,), dtype=torch.int64, device=device)
+        q64 = q[0].double()
+        for s0 in range(0, n, chunk):
+            sc = rows_of(s0).double() @ q64
+            best_s = torch.cat([best_s, sc])
+            best_i = torch.cat([best_i, torch.arange(s0, s0 + sc.numel(), device=device)])
+            top = torch.topk(best_s, min(4 * k, best_s.numel()))
+            best_s, best_i = top.values, best_i[top.indices]
+        ref_s, ref_i = best_s.cpu().numpy(), best_i.cpu().numpy()
+        score_of = dict(zip(ref_i.tolist(), ref_s.tolist()))
+        kth = ref_s[k - 1]
+        err = max(abs(float(Dx[0, j]) - score_of.get(int(Ix[0, j]), float("nan"))) for j in range(k))
+        bad = sum(1 for j in range(k) if int(Ix[0, j]) not in score_of or score_of[int(Ix[0, j])] < kth - 4e-6)
+        out["parity_check"] = {"setting": f"nprobe = nlist = {nlist} (exhaustive)", "rows_checked": n, "max_abs_err": err,
+                               "violations": int(bad), "sorted": bool(np.all(np.diff(Dx[0]) <= 0)), "score_tol": 1e-5,
+                               "tie_band": 4e-6,
+                               "ok": bool(err <= 1e-5 and bad == 0 and np.all(np.diff(Dx[0]) <= 0)
+                                          and all(v["same_bytes_as_two_launches"] for v in per.values()))}
+    except Exception as e:  # noqa: BLE001 - reported, never raised
+        out["error"] = repr(e)[:400]
+    finally:
+        if saved is None:
+            os.environ.pop("WB_IVF_FUSE_COARSE", None)
+        else:
+            os.environ["WB_IVF_FUSE_COARSE"] = saved
+    return out
+
+
 def parity_check(src, lo, hi, q, D, I, k, world, device, allowed=None):
     """Verify (D, I) = global top-k of queries q (all [*, .] device tensors, identical on every rank) against an fp64
     pass over THIS rank's regenerated rows; partial counts are summed over the ranks.  Returns a dict (rank-identical).
@@ -660,6 +765,8 @@ def run_ours(a):
         if not a.no_parity:
             entry["parity_check"] = parity_check(src, lo, hi, qb_last, Db, Ib, a.k, world, device)
         secondary[f"batch{b}"] = entry
+    if a.secondary == "auto" and world == 1 and a.batch == 1:
+        secondary["ivf_one_query"] = ivf_one_query_secondary(device, a.k)
 
     if rank == 0:
         line = {
