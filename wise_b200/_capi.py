@@ -111,4 +111,7 @@ def ptr(a) -> int | None:
         return None
     if hasattr(a, "data_ptr"):
         return a.data_ptr()
-    return a.ctypes.data
+    try:  # writable contiguous numpy array: the buffer protocol is twice as fast as ndarray.ctypes (3 pointers per search)
+        return C.addressof(C.c_char.from_buffer(a))
+    except (TypeError, ValueError):  # read-only, empty or strided: the slow, general way
+        return a.ctypes.data
