@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 BINS = 1024
+RESOLVE_MAX = 256
 
 
 def order_f32(x: np.ndarray) -> np.ndarray:
@@ -59,6 +60,14 @@ def select_top_keys(okeys: np.ndarray, need0: int) -> tuple[list[int], int]:
                 sel.append(k)
         if last:
             return sel, p + 1
+        if cnt <= RESOLVE_MAX:  # small boundary bin: the best `need - above` of its keys by rank counting, no further pass
+            binkeys = [k for k in inside if (k - lo) >> sh == bstar]
+            assert len(binkeys) == cnt
+            want = need - above
+            for k in binkeys:
+                if sum(1 for u in binkeys if u > k) < want:
+                    sel.append(k)
+            return sel, p + 1
         assert sh > 0, "a width-1 bin holds one key (keys are distinct)"
         nlo = lo + (bstar << sh)
         nhi = min(hi, nlo + (1 << sh) - 1)
@@ -102,10 +111,16 @@ def test_ties_go_to_the_lower_list_id():
     assert ids == list(range(10))
 
 
-def test_gaussian_scores_take_two_or_three_passes():
+def test_gaussian_scores_take_one_pass():
     rng = np.random.default_rng(5)
     passes = []
     for _ in range(20):
         okeys = order_f32(rng.standard_normal(4096).astype(np.float32) * 0.05)
         passes.append(select_top_keys(okeys, 32)[1])
-    assert max(passes) <= 3, passes
+    assert max(passes) == 1, passes
+
+
+def test_large_boundary_bins_still_recurse():
+    okeys = order_f32(np.zeros(4096, np.float32))  # every key in one bin of 4096 > RESOLVE_MAX
+    sel, passes = select_top_keys(okeys, 10)
+    assert passes >= 2 and sorted(0xFFFFFFFF - (k & 0xFFFFFFFF) for k in sel) == list(range(10))

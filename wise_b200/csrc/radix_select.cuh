@@ -9,14 +9,16 @@
 // Every pass histograms the keys of the current range [lo, hi] into <= 1024 equal-width bins, takes every bin above the
 // one that holds the need-th largest key, and either finishes (that bin is taken whole) or recurses into it.  The first
 // range is [min key, max key], so the bins resolve the score distribution at once; a range shrinks by >= 2^10 per pass
-// and a width-1 bin holds one key, so the loop ends after at most 7 passes.  The k winners are then bitonic-sorted
-// (128 keys for k = 100) by the caller.  tests/test_coarse_model.py checks the arithmetic on the CPU.
+// and a width-1 bin holds one key, so the loop ends after at most 7 passes; in practice after ONE, because a boundary bin
+// of up to 256 keys is resolved on the spot by rank counting.  The winners are then ordered by the caller.
+// tests/test_coarse_model.py checks the arithmetic on the CPU.
 #pragma once
 #include "common.cuh"
 
 namespace wb {
 
 constexpr int kSelBins = 1024;  // histogram bins of one selection pass (32 chunks of 32)
+constexpr int kRadixResolveMax = 256;  // a boundary bin of up to this many keys is resolved by rank counting (fits the histogram's memory)
 
 // Shared-memory scratch of one selection (the caller places it; 16-byte aligned).
 constexpr size_t kRadixScratchBytes = (size_t)kSelBins * 4 + 32 * 4 + 1024;
@@ -132,21 +134,39 @@ __device__ __forceinline__ int block_radix_select(int n, int need0, KeyAt key_at
                 ctl[2] = cstar * 32 + bl;
                 ctl[3] = (int)(ge - cnt);
                 ctl[4] = (int)cnt;
+                ctl[5] = 0;  // keys collected from the boundary bin
             }
         }
         rs_sync<NT>(bar_id);
         const uint32_t bstar = (uint32_t)ctl[2];
         const int above = ctl[3], cnt = ctl[4];
         const bool last = cnt == need - above;  // the boundary bin is taken whole: done
+        // A small boundary bin is resolved on the spot instead of by another histogram pass (a pass costs ~2 us of
+        // barriers whatever it counts): its keys are collected - the histogram is dead by now, its memory holds them -
+        // and the best `need - above` of them are found by rank counting.
+        const bool resolve = !last && cnt <= kRadixResolveMax;
+        uint64_t* binkeys = reinterpret_cast<uint64_t*>(hist);
         for (int i = tid; i < n; i += NT) {
             const uint64_t kk = key_at(i);
             if (kk >= lo && kk <= hi) {
                 const uint32_t b = (uint32_t)((kk - lo) >> sh);
                 if (b > bstar || (last && b == bstar)) sel[atomicAdd(&ctl[0], 1)] = kk;
+                else if (resolve && b == bstar) binkeys[atomicAdd(&ctl[5], 1)] = kk;
             }
         }
         rs_sync<NT>(bar_id);
         if (last) break;
+        if (resolve) {
+            const int want = need - above;
+            for (int t = tid; t < cnt; t += NT) {
+                const uint64_t kk = binkeys[t];
+                int rank = 0;
+                for (int u = 0; u < cnt; ++u) rank += binkeys[u] > kk;
+                if (rank < want) sel[atomicAdd(&ctl[0], 1)] = kk;
+            }
+            rs_sync<NT>(bar_id);
+            break;
+        }
         if (tid == 0) {
             const uint64_t nlo = lo + ((uint64_t)bstar << sh);
             uint64_t nhi = nlo + (((uint64_t)1 << sh) - 1);
